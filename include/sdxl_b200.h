@@ -1,0 +1,183 @@
+/* sdxl_b200.h — C ABI of the B200-native SDXL denoising engine (libsdxl_b200.so).
+ *
+ * This is the drop-in boundary for the diffusion sampling path of Gadersd/stable-diffusion-xl-burn:
+ * the entry points a Rust `src/backend.rs` replacement would bind with `extern "C"` (see
+ * INTEGRATION.md for the shim). Each function names the reference interface it replaces; citations
+ * are file:line relative to the reference repository root.
+ *
+ * Conventions
+ *  - Status: every function returns 0 on success, non-zero on error; `sdxl_last_error(ctx)` returns a
+ *    human-readable message for the last failure on that context. No exception crosses the boundary
+ *    (the reference panics on shape errors; here they are status codes).
+ *  - Pointers are DEVICE pointers unless the parameter name ends in `_host` or the struct says so.
+ *    Inputs are borrowed for the duration of the call; outputs are caller-allocated.
+ *  - Tensors are contiguous. Public activations use the reference's layouts: NCHW for images/latents,
+ *    [B,T,C] for token tensors, f16 (`uint16_t` bit pattern of IEEE binary16 == burn's `f16`) unless
+ *    stated; NHWC/f32 is internal.
+ *  - One sdxl_ctx per (device, stream). A ctx and the objects created from it are not thread-safe;
+ *    independent ctxs are fully concurrent. All work is enqueued on the ctx stream; functions that
+ *    return results to host memory synchronise that stream, all others are asynchronous.
+ *  - There is NO CPU fallback: on a machine without an sm_100 GPU sdxl_ctx_create fails.
+ */
+#ifndef SDXL_B200_H_
+#define SDXL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SDXL_API __attribute__((visibility("default")))
+#else
+#define SDXL_API
+#endif
+
+typedef uint16_t sdxl_half; /* IEEE binary16 bit pattern */
+typedef struct sdxl_ctx sdxl_ctx;
+typedef struct sdxl_unet sdxl_unet;
+
+#define SDXL_MAX_LEVELS 8
+
+/* Mirrors DiffuserConfig (src/model/stablediffusion/mod.rs:269-278) + UNetConfig
+ * (src/model/unet/mod.rs:59-69). Transformer blocks exist on levels 1 and 2 only
+ * (unet/mod.rs:125,264); transformer_depths[level] is read for those levels, and
+ * transformer_depths[n_levels-1] is the middle-block depth (unet/mod.rs:239). */
+typedef struct sdxl_unet_cfg {
+  int32_t adm_in_channels;                    /* 2816 base / 2560 refiner */
+  int32_t in_channels;                        /* 4 */
+  int32_t out_channels;                       /* 4 */
+  int32_t model_channels;                     /* 320 base / 384 refiner */
+  int32_t n_levels;                           /* len(channel_mults) */
+  int32_t channel_mults[SDXL_MAX_LEVELS];     /* [1,2,4] base */
+  int32_t n_head_channels;                    /* 64 (this build requires 64) */
+  int32_t transformer_depths[SDXL_MAX_LEVELS];/* [_,2,10] base */
+  int32_t context_dim;                        /* 2048 base / 1280 refiner */
+  int32_t is_refiner;                         /* Diffuser.is_refiner: single forward, no CFG */
+  int32_t n_steps;                            /* 1000 (stablediffusion/mod.rs:282) */
+} sdxl_unet_cfg;
+
+/* Mirrors Conditioning (src/model/stablediffusion/mod.rs:544-555); f16 like the reference's
+ * Diffuser<LibTorch<f16>> after Conditioning::convert (src/bin/sample/main.rs:236-237).
+ * n_batch images share the unconditional rows (the reference repeats them, mod.rs:535-536). */
+typedef struct sdxl_conditioning {
+  int32_t on_host;        /* 0: pointers are device memory, 1: host memory */
+  int32_t n_batch;        /* context_full.dims()[0] */
+  int32_t n_ctx;          /* 77 */
+  const sdxl_half* context_full;                        /* [n_batch, n_ctx, 2048] */
+  const sdxl_half* context_open_clip;                   /* [n_batch, n_ctx, 1280] */
+  const sdxl_half* unconditional_context_full;          /* [n_ctx, 2048] */
+  const sdxl_half* unconditional_context_open_clip;     /* [n_ctx, 1280] */
+  const sdxl_half* channel_context;                     /* [n_batch, 2816] */
+  const sdxl_half* channel_context_refiner;             /* [n_batch, 2560] */
+  const sdxl_half* unconditional_channel_context;       /* [2816] */
+  const sdxl_half* unconditional_channel_context_refiner; /* [2560] */
+  int32_t resolution[2];  /* (height, width) in pixels; latent is /8 */
+} sdxl_conditioning;
+
+/* ---- context -------------------------------------------------------------------------------- */
+/* Replaces the reference's fixed `LibTorchDevice::Cuda(0)` + libtorch default stream
+ * (src/bin/sample/main.rs:131). cuda_stream may be NULL (the ctx creates its own). */
+SDXL_API int sdxl_ctx_create(int device, void* cuda_stream, sdxl_ctx** out);
+SDXL_API void sdxl_ctx_destroy(sdxl_ctx* ctx);
+SDXL_API const char* sdxl_last_error(const sdxl_ctx* ctx);
+SDXL_API int sdxl_ctx_synchronize(sdxl_ctx* ctx);
+/* Number of this library's kernels launched on the ctx since creation (bench `gpu_launches`). */
+SDXL_API uint64_t sdxl_ctx_launch_count(const sdxl_ctx* ctx);
+
+/* ---- UNet / Diffuser ------------------------------------------------------------------------ */
+/* Replaces load_diffuser_model (src/bin/sample/main.rs:35-41): builds the device-resident model from
+ * a flat weight pack (format: DESIGN.md "weight pack"; tensor names = the reference's npy dump tree,
+ * src/model/unet/load.rs, values f16 like the .mpk). The pack may live in host or device memory
+ * (pack_on_device); the library keeps its own re-laid-out copy, the caller may free the pack. */
+SDXL_API int sdxl_unet_load(sdxl_ctx* ctx, const sdxl_unet_cfg* cfg, const void* pack, size_t bytes,
+                   int pack_on_device, sdxl_unet** out);
+SDXL_API void sdxl_unet_destroy(sdxl_unet* unet);
+/* Step-invariant part of UNet::forward, hoisted: cross-attention K/V projections of `context`
+ * (unet/mod.rs:1010-1011 for attn2) and the label-embedding MLP (unet/mod.rs:464-466).
+ * context [B, n_ctx, context_dim] f16, y [B, adm_in_channels] f16. */
+SDXL_API int sdxl_unet_set_conditioning(sdxl_unet* unet, int B, int n_ctx, const sdxl_half* context,
+                               const sdxl_half* y);
+/* == UNet::forward (src/model/unet/mod.rs:449-493) with the conditioning set above.
+ * x [B,4,h,w] NCHW f16, t_host: the single timestep the reference passes as Int[1]
+ * (stablediffusion/mod.rs:416), eps_out [B,4,h,w] NCHW f16 (caller-owned). */
+SDXL_API int sdxl_unet_forward(sdxl_unet* unet, int B, int h, int w, const sdxl_half* x, int32_t t_host,
+                      sdxl_half* eps_out);
+/* Same, f32 NCHW in/out (no input/output rounding; used by the parity tests). */
+SDXL_API int sdxl_unet_forward_f32(sdxl_unet* unet, int B, int h, int w, const float* x, int32_t t_host,
+                          float* eps_out);
+
+/* == Diffuser::sample_latent / sample_latent_with_inpainting / refine_latent
+ * (src/model/stablediffusion/mod.rs:317-376) and the DDIM loops they call (:390-483), including
+ * forward_diffuser's classifier-free guidance (:494-541; both branches are evaluated as one batched
+ * forward, the combine keeps the reference's u + (c-u)*s form).
+ *  step_start : 0 for sample_latent; refine_latent's step_start (e.g. 800) otherwise. When
+ *               step_start > 0 `init_latent` is the latent to refine and is noised as mod.rs:363-367.
+ *  init_latent: [n_batch,4,H/8,W/8] f32 NCHW. For step_start == 0 this is the initial noise
+ *               (gen_noise, mod.rs:378-388); NULL => seeded Philox N(0,1) (stream seed, subsequence 0).
+ *  noise      : optional injected per-call noise [n_noise,n_batch,4,H/8,W/8] f32 (refine entry noise
+ *               and, for inpainting, one tensor per step in loop order); NULL => seeded Philox.
+ *  inpaint_ref/inpaint_mask: both NULL, or reference latent f32 and mask bytes (1 = keep generated,
+ *               mask_where semantics of mod.rs:465), each [n_batch,4,H/8,W/8].
+ *  latent_out : [n_batch,4,H/8,W/8] f32 NCHW, device (or host if cond->on_host).
+ * All pointer arguments live where cond->on_host says. */
+SDXL_API int sdxl_sample_latent(sdxl_unet* unet, const sdxl_conditioning* cond, double guidance_scale,
+                       int n_steps, int step_start, const float* init_latent, const float* noise,
+                       int n_noise, uint64_t seed, const float* inpaint_ref,
+                       const uint8_t* inpaint_mask, float* latent_out);
+
+/* Step-wise control for benchmarking / external loops: */
+/* prepare a sampler state for cond (uploads + hoists conditioning, allocates the latent). */
+SDXL_API int sdxl_sampler_begin(sdxl_unet* unet, const sdxl_conditioning* cond, double guidance_scale);
+/* == one iteration of the loop body at timestep t (alpha lookups + forward_diffuser + DDIM update)
+ * on the internal latent; t_prev < 0 means alpha_prev = 1.0 (mod.rs:408-412). Asynchronous. */
+SDXL_API int sdxl_sampler_step(sdxl_unet* unet, int t, int t_prev);
+/* Same, but the latent comes from / goes to HOST memory inside the call (end-to-end timing):
+ * latent_host [n_batch,4,h,w] f32 in, updated in place. Synchronises the stream. */
+SDXL_API int sdxl_sampler_step_host(sdxl_unet* unet, int t, int t_prev, float* latent_host);
+SDXL_API int sdxl_sampler_set_latent(sdxl_unet* unet, const float* latent, int on_host);
+SDXL_API int sdxl_sampler_get_latent(sdxl_unet* unet, float* latent, int on_host);
+/* alphas_cumprod[i] as the sampler sees it (f16-stored like the reference's .mpk, widened). */
+SDXL_API double sdxl_unet_alpha(const sdxl_unet* unet, int i);
+/* Algorithmic FLOPs (2*MAC over Linear/conv/attention, SURVEY 8(d) counting rule) and kernel-op count of
+ * the launch plan currently built for this UNet (0 before the first forward). */
+SDXL_API double sdxl_unet_plan_flops(const sdxl_unet* unet);
+SDXL_API int sdxl_unet_plan_num_ops(const sdxl_unet* unet);
+/* seeded N(0,1) exactly as the sampler generates it (device out). */
+SDXL_API int sdxl_randn(sdxl_ctx* ctx, float* out, size_t n, uint64_t seed, uint64_t subsequence);
+
+/* ---- operator level (== the burn ops / Backend hooks the hot path is built from) ------------ */
+/* == Backend::qkv_attention (src/backend.rs:4-10, libtorch impl :32-79, generic :88-128).
+ * q [B,T,C], k/v [B,S,C] f16, C = n_head*64, mask must be NULL (the UNet never passes one,
+ * unet/mod.rs:1017). out [B,T,C] f16. */
+SDXL_API int sdxl_qkv_attention(sdxl_ctx* ctx, const sdxl_half* q, const sdxl_half* k, const sdxl_half* v,
+                       const sdxl_half* mask, int B, int T, int S, int C, int n_head, sdxl_half* out);
+/* == nn::Linear::forward: x [M,K] f16, w [K,N] f16 ([in,out], python/save.py:20-25), bias [N] f16 or
+ * NULL, residual [M,N] f32 or NULL; out f32 [M,N] (out_f16 = 0) or f16. geglu != 0 => N is the fused
+ * 2*n_out projection and out is [M,N/2] f16 = h[:, :N/2] * gelu_erf(h[:, N/2:]) (unet/mod.rs:942-956). */
+SDXL_API int sdxl_op_linear(sdxl_ctx* ctx, const sdxl_half* x, const sdxl_half* w, const sdxl_half* bias,
+                   const float* residual, int M, int K, int N, int geglu, int out_f16, void* out);
+/* == nn::conv::Conv2d::forward on NHWC data: x [B,H,W,Cin] f32, w OIHW f16 (python/save.py:56-72),
+ * bias [Cout] f16 or NULL; ksize 1|3 (pad = ksize/2), stride 1|2 (Downsample, unet/mod.rs:760-774),
+ * upsample != 0 => nearest-2x first (Upsample::forward, unet/mod.rs:742-751). out f32 NHWC. */
+SDXL_API int sdxl_op_conv2d(sdxl_ctx* ctx, const float* x, const sdxl_half* w, const sdxl_half* bias, int B, int H,
+                   int W, int Cin, int Cout, int ksize, int stride, int upsample, float* out);
+/* == GroupNorm::forward (+ optional SILU::forward) on NHWC f32 [B,HW,C] (groupnorm/mod.rs:52-82,
+ * silu.rs:14-16); x2 (nullable) is channel-concatenated after x1 (Tensor::cat, unet/mod.rs:484).
+ * out f16 [B,HW,C1+C2]. */
+SDXL_API int sdxl_op_group_norm(sdxl_ctx* ctx, const float* x1, int C1, const float* x2, int C2, int B, int HW,
+                       int n_group, const float* gamma, const float* beta, float eps, int silu,
+                       sdxl_half* out);
+/* == LayerNorm::forward (layernorm/mod.rs:34-49): x [rows,C] f32 -> f16. */
+SDXL_API int sdxl_op_layer_norm(sdxl_ctx* ctx, const float* x, const float* gamma, const float* beta, float eps,
+                       int rows, int C, sdxl_half* out);
+/* == timestep_embedding (unet/mod.rs:21-39): t_host[n] ints -> out [n,dim] f32 (cos half, sin half). */
+SDXL_API int sdxl_op_timestep_embedding(sdxl_ctx* ctx, const int32_t* t_host, int n, int dim, int max_period,
+                               float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDXL_B200_H_ */

@@ -1,0 +1,149 @@
+// Host-side launch API of the sm_100a kernels (internal to libsdxl_b200.so; the public boundary is
+// include/sdxl_b200.h). All pointers are device pointers. All launchers return cudaError_t-style
+// int (0 = ok) and never synchronise.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sdxl {
+
+// ------------------------------------------------------------------------------------------------
+// Implicit GEMM on tcgen05 (igemm.cu): out[pixel, n] = epilogue( sum_seg sum_c A_seg[pixel+tap, c] *
+// Wt[n, k(seg,c)] ). Linear layers are the 1-segment / 1x1 case of the same kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr int IGEMM_MAX_SEG = 12;
+struct IgemmSeg {
+  int16_t map;   // 0 -> tmA0, 1 -> tmA1
+  int16_t dw, dh;  // tap offset added to the tile's (w0,h0)
+  int16_t db;    // offset added to the tile's batch coordinate (stride-2 phase images)
+  int32_t nkb;   // number of 64-channel K blocks in this segment
+};
+enum IgemmMode : int { IGEMM_LINEAR = 0, IGEMM_GEGLU = 1 };
+struct alignas(64) IgemmParams {
+  CUtensorMap tmA0, tmA1, tmB;
+  IgemmSeg seg[IGEMM_MAX_SEG];
+  int nseg;
+  int Wt, Ht, Bt;             // A box in pixels, Wt*Ht*Bt == 128
+  int W, H, Bn;               // output extents
+  int tilesW, tilesH, tilesB;
+  int N;                      // valid output columns (GEGLU: columns of the fused [value|gate] GEMM)
+  int BN;                     // N tile (multiple of 16, <= 256)
+  int nstages;
+  int mode;                   // IgemmMode
+  void* out;                  // f16 or f32 [pixels, ldo]
+  int out_f32;
+  int ldo;
+  const float* bias;          // nullable; index b*bias_bstride + n
+  int bias_bstride;
+  const float* res;           // nullable f32 residual [pixels, ldr]
+  int ldr;
+};
+// A operand view: NHWC f16 tensor [Bn, H, W, C] with channel pitch `pitch` (elements, multiple of 8).
+int make_tmap_act(CUtensorMap* tm, const __half* base, int Bn, int H, int W, int C, int pitch, int Wt,
+                  int Ht, int Bt);
+// B operand view: K-major weights [N, K] f16 with row pitch K (multiple of 8); box (64, BN).
+int make_tmap_wgt(CUtensorMap* tm, const __half* base, int N, int K, int BN);
+// Picks Wt/Ht/Bt (product 128) for an output image of W x H.
+void igemm_pick_box(int W, int H, int* Wt, int* Ht, int* Bt);
+// Fills tiles*/nstages from the other fields and launches.
+int igemm_launch(cudaStream_t st, IgemmParams& p);
+// Chooses an N tile for (M pixels, N columns) minimising wave-quantisation loss on `num_sms` SMs.
+int igemm_pick_bn(int m_tiles, int N, int num_sms, bool geglu);
+
+// ------------------------------------------------------------------------------------------------
+// Attention (attention.cu): out[b, t, h*64:(h+1)*64] = softmax(q k^T / 8) v, head dim 64.
+// q/k/v are column windows of row-major f16 matrices (fused QKV / KV GEMM outputs).
+// ------------------------------------------------------------------------------------------------
+struct AttnParams {
+  CUtensorMap tmQ, tmK, tmV;  // 3D maps (64 cols, rows, batch)
+  int T, S, n_head, B;
+  int q_col0, k_col0, v_col0;  // column of head 0 inside each matrix
+  __half* out;                 // [B*T, ldo]
+  int ldo;
+  float scale_log2e;           // (1/sqrt(d)) * log2(e)
+};
+int make_tmap_rows(CUtensorMap* tm, const __half* base, int rows_per_batch, int nbatch, int cols, int pitch);
+int attention_launch(cudaStream_t st, const AttnParams& p);
+
+// ------------------------------------------------------------------------------------------------
+// Norms (norm.cu)
+// ------------------------------------------------------------------------------------------------
+// GroupNorm over NHWC f32 input (optionally the channel-concatenation of two tensors), 32 groups,
+// biased variance, eps inside the sqrt (reference groupnorm/mod.rs:52-82). Writes f16.
+struct GnParams {
+  const float* x1; int C1;    // [B, HW, C1]
+  const float* x2; int C2;    // nullable, [B, HW, C2]  (cat([x1, x2], channel))
+  int B, HW, n_group;
+  const float* gamma; const float* beta;  // [C1+C2]
+  float eps;
+  int silu;                   // apply x*sigmoid(x) after the affine
+  __half* y;                  // [B, HW, C1+C2] normalised (+SiLU) output
+  __half* raw;                // nullable: un-normalised f16 copy of cat([x1,x2]) (skip-conv operand)
+  float* partial;             // scratch [B, nchunk, n_group, 2]
+  int nchunk;                 // filled by gn_launch
+};
+size_t gn_scratch_floats(int B, int n_group);
+int gn_launch(cudaStream_t st, GnParams& p);
+// LayerNorm over the last dim of f32 [rows, C] -> f16 [rows, C] (reference layernorm/mod.rs:34-49).
+int layernorm_launch(cudaStream_t st, const float* x, const float* gamma, const float* beta, float eps,
+                     int rows, int C, __half* y);
+
+// ------------------------------------------------------------------------------------------------
+// Small / elementwise kernels (elementwise.cu)
+// ------------------------------------------------------------------------------------------------
+// out[b,n] = act( dot(in[b,:], W[n,:]) + bias[n] + add[b*add_bstride + n] ); W f16 [N,ldw] K-major (row pitch ldw >= K).
+// in_silu: apply SiLU to the input on load. out_silu: SiLU on the output.
+int gemv_launch(cudaStream_t st, const float* in, int in_bstride, int Bv, int K, const __half* W, int ldw,
+                const float* bias, const float* add, int add_bstride, int N, int in_silu, int out_silu,
+                float* out, int out_bstride);
+// timestep_embedding (reference unet/mod.rs:21-39): out[b, :] = [cos(t*f_i), sin(t*f_i)], dim even.
+int timestep_embedding_launch(cudaStream_t st, const int* t_dev, int nt, int dim, float max_period,
+                              float* out);
+// First conv: x NCHW f16 [B,Cin,H,W] (Cin<=8) -> NHWC f32 [B,H,W,Cout], 3x3 pad 1. w: [Cout][3][3][Cin] f32.
+int conv_in_launch(cudaStream_t st, const __half* x, int B, int Cin, int H, int W, const float* w,
+                   const float* bias, int Cout, float* y);
+// general form: x f16 or f32 NCHW with Bx images; output batch b reads image b % Bx.
+int conv_in_launch_t(cudaStream_t st, const void* x, int x_f32, int Bx, int B, int Cin, int H, int W,
+                     const float* w, const float* bias, int Cout, float* y);
+// Nearest-2x upsample of NHWC: f32 [B,H,W,C] -> f16 [B,2H,2W,C] (reference unet/mod.rs:742-751).
+int upsample2x_launch(cudaStream_t st, const float* x, int B, int H, int W, int C, __half* y);
+// Stride-2 phase split: f32 [B,H,W,C] -> f16 [4(phase=ph*2+pw), B, H/2, W/2, C]; phase image
+// P[ph][pw][i][j] = x[2i+ph][2j+pw].
+int phase_split_launch(cudaStream_t st, const float* x, int B, int H, int W, int C, __half* y);
+int cast_f32_to_f16_launch(cudaStream_t st, const float* x, size_t n, __half* y);
+int cast_f16_to_f32_launch(cudaStream_t st, const __half* x, size_t n, float* y);
+// eps NHWC f32 [B,HW,ldx] (first C valid) -> NCHW [B,C,HW], f16 or f32 output
+int nhwc_to_nchw_f16_launch(cudaStream_t st, const float* x, int B, int HW, int C, int ldx, __half* y);
+int nhwc_to_nchw_f32_launch(cudaStream_t st, const float* x, int B, int HW, int C, int ldx, float* y);
+// Sampler elementwise (reference stablediffusion/mod.rs:407-428, 463-465, 539-540).
+// eps layout: NHWC f32 [nfwd*Bimg, HW, ld]; cond rows first, then uncond (if cfg).
+// x: NCHW f32 master latent [Bimg,C,HW], updated in place; x16: f16 NCHW copy duplicated for the next
+// forward ([nfwd*Bimg, C, HW]).
+int cfg_ddim_launch(cudaStream_t st, const float* eps, int ld, int Bimg, int C, int HW, int use_cfg,
+                    float guidance, float sqrt_a, float sqrt_1ma, float sqrt_ap, float sqrt_1map,
+                    float* x, __half* x16);
+// x = mask ? x : ref*sqrt_a + noise*sqrt_1ma ; also refreshes x16 (both forwards).
+int inpaint_blend_launch(cudaStream_t st, float* x, const float* ref, const float* noise,
+                         const uint8_t* mask, size_t n_per_img_batch, int nfwd, float sqrt_a,
+                         float sqrt_1ma, __half* x16);
+// x = x*sa + noise*sb  (refine_latent entry, reference stablediffusion/mod.rs:363-367)
+int axpby_launch(cudaStream_t st, float* x, const float* noise, size_t n, float sa, float sb);
+// Standard normal noise, Philox4x32-10 + Box-Muller, element i of stream (seed, subseq).
+int randn_launch(cudaStream_t st, float* out, size_t n, uint64_t seed, uint64_t subseq);
+int dup_latent_f16_launch(cudaStream_t st, const float* x, size_t n, int nfwd, __half* x16);
+
+// Weight re-layout at load time (elementwise.cu)
+// Linear [K(in), N(out)] row-major f16 -> K-major [N, Kpad] f16 (zero padded), dst row pitch Kpad;
+// rows written at dst_row0 + perm(n) where perm handles the GEGLU value/gate interleave (geglu_bn>0).
+int transpose_linear_launch(cudaStream_t st, const __half* src, int K, int N, __half* dst, int Kpad,
+                            int dst_row0, int geglu_bn);
+// Conv OIHW f16 -> [O, (kh,kw,I padded to Ipad)] f16 at column offset col0 of a [O, Ktot] matrix.
+int repack_conv_launch(cudaStream_t st, const __half* src, int O, int I, int KH, int KW, __half* dst,
+                       int Ktot, int col0, int Ipad);
+int vec_add_f32_launch(cudaStream_t st, float* dst, const float* src, int n);  // dst += src
+// bias f16 [N] -> f32, optional GEGLU permutation, optional accumulate (dst += src).
+int bias_to_f32_launch(cudaStream_t st, const __half* src, int N, float* dst, int geglu_bn, int accumulate);
+
+}  // namespace sdxl

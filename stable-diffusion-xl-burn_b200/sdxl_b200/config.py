@@ -1,0 +1,100 @@
+"""Model configurations (mirror of the reference's DiffuserConfig / UNetConfig).
+
+reference: src/model/stablediffusion/mod.rs:269-306 (DiffuserConfig), src/model/unet/mod.rs:59-69
+(UNetConfig). The `.cfg` JSON files live on HuggingFace, not in the reference repo; the values below
+are the ones SURVEY.md section 5 derives from the code and dump scripts.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Tuple
+
+
+@dataclass(frozen=True)
+class UNetConfig:
+    adm_in_channels: int
+    model_channels: int
+    channel_mults: Tuple[int, ...]
+    transformer_depths: Tuple[int, ...]
+    context_dim: int
+    is_refiner: bool = False
+    in_channels: int = 4
+    out_channels: int = 4
+    n_head_channels: int = 64
+    n_steps: int = 1000
+
+    @property
+    def n_levels(self) -> int:
+        return len(self.channel_mults)
+
+    @property
+    def time_embed_dim(self) -> int:
+        return 4 * self.model_channels
+
+
+# SDXL base: diffuser.cfg
+SDXL_BASE = UNetConfig(adm_in_channels=2816, model_channels=320, channel_mults=(1, 2, 4),
+                       transformer_depths=(0, 2, 10), context_dim=2048, is_refiner=False)
+# SDXL refiner: refiner.cfg (middle depth = transformer_depths[-1] = 4, inferred)
+SDXL_REFINER = UNetConfig(adm_in_channels=2560, model_channels=384, channel_mults=(1, 2, 4, 4),
+                          transformer_depths=(0, 4, 4, 4), context_dim=1280, is_refiner=True)
+# Tiny config for known-answer tests (the reference's `test_tiny_unet` probe method,
+# src/bin/test/main.rs:128-140): same topology rules (transformers on levels 1 and 2, head dim 64).
+TINY = UNetConfig(adm_in_channels=8, model_channels=64, channel_mults=(1, 2, 4),
+                  transformer_depths=(0, 1, 2), context_dim=24, is_refiner=False)
+TINY_REFINER = UNetConfig(adm_in_channels=16, model_channels=64, channel_mults=(1, 2, 4),
+                          transformer_depths=(0, 1, 1), context_dim=40, is_refiner=True)
+
+
+@dataclass
+class BlockSpec:
+    kind: str              # conv | resnet | downsample | resnet_transformer | resnet_transformer_upsample | resnet_upsample
+    path: str
+    c_in: int
+    c_out: int
+    depth: int = 0         # transformer depth
+    n_head: int = 0
+
+
+def block_program(cfg: UNetConfig) -> Tuple[List[BlockSpec], BlockSpec, List[BlockSpec]]:
+    """Input / middle / output block lists exactly as UNetConfig::init builds them
+    (reference src/model/unet/mod.rs:115-173, 238-248, 250-328)."""
+    mc = cfg.model_channels
+    nl = cfg.n_levels
+    ins: List[BlockSpec] = [BlockSpec("conv", "input_blocks/0", cfg.in_channels, mc)]
+    idx = 1
+    for level in range(nl):
+        c_in = cfg.channel_mults[max(level - 1, 0)] * mc
+        c_out = cfg.channel_mults[level] * mc
+        tr = level in (1, 2)
+        for k in range(2):
+            ci = c_in if k == 0 else c_out
+            if tr:
+                ins.append(BlockSpec("resnet_transformer", f"input_blocks/{idx}", ci, c_out,
+                                     cfg.transformer_depths[level], c_out // cfg.n_head_channels))
+            else:
+                ins.append(BlockSpec("resnet", f"input_blocks/{idx}", ci, c_out))
+            idx += 1
+        if level != nl - 1:
+            ins.append(BlockSpec("downsample", f"input_blocks/{idx}", c_out, c_out))
+            idx += 1
+    cm = cfg.channel_mults[-1] * mc
+    mid = BlockSpec("middle", "middle_block", cm, cm, cfg.transformer_depths[-1], cm // cfg.n_head_channels)
+    outs: List[BlockSpec] = []
+    idx = 0
+    for level in reversed(range(nl)):
+        next_level = level + 1 if level != nl - 1 else level
+        c_out = cfg.channel_mults[level] * mc
+        cins = (cfg.channel_mults[next_level] * mc + c_out, 2 * c_out,
+                c_out + cfg.channel_mults[max(level - 1, 0)] * mc)
+        tr = level in (1, 2)
+        for k in range(3):
+            up = k == 2 and (tr or level != 0)
+            if tr:
+                kind = "resnet_transformer_upsample" if up else "resnet_transformer"
+                outs.append(BlockSpec(kind, f"output_blocks/{idx}", cins[k], c_out,
+                                      cfg.transformer_depths[level], c_out // cfg.n_head_channels))
+            else:
+                outs.append(BlockSpec("resnet_upsample" if up else "resnet", f"output_blocks/{idx}", cins[k], c_out))
+            idx += 1
+    return ins, mid, outs

@@ -1,0 +1,166 @@
+"""Weight naming, deterministic synthetic weights and the flat weight pack.
+
+Tensor names and layouts follow the reference's npy dump tree (src/model/unet/load.rs, python/save.py):
+Linear `weight` is [in, out] (save.py:20-25 transposes PyTorch's), conv `weight` is OIHW (save.py:56-72),
+norms have `weight`/`bias` [C]; values are f16 like the shipped `.mpk` (HalfPrecisionSettings,
+src/bin/convert/main.rs:65-70). `alphas_cumprod` is the LegacyDDPMDiscretization schedule
+(python/dump.py:29-36), also stored f16.
+
+No SDXL checkpoint exists offline, so benchmarks and parity tests use the synthetic initialisation of
+SURVEY.md 8(d): W ~ N(0, 1/fan_in), residual-branch output projections scaled down, biases ~ N(0, 0.02^2),
+gamma = 1 + N(0, 0.05^2), beta ~ N(0, 0.05^2); one master seed.
+
+Pack format ("SDXLPK01"): header {magic[8], u32 n_tensors, u32 0, u64 data_offset}, n_tensors entries
+{char name[120], u32 dtype(0=f16), u32 ndim, u64 shape[4], u64 offset, u64 nbytes}, data (256B aligned).
+"""
+from __future__ import annotations
+
+import struct
+from typing import Dict, Iterable, List, Tuple
+
+import numpy as np
+import torch
+
+from .config import UNetConfig, block_program
+
+Spec = Tuple[str, Tuple[int, ...], str, float]  # name, shape, kind, scale
+
+RESID_SCALE = 0.2
+
+
+def _res_specs(path: str, c_in: int, c_out: int, ted: int) -> List[Spec]:
+    s: List[Spec] = [
+        (f"{path}/norm_in/weight", (c_in,), "gamma", 1.0), (f"{path}/norm_in/bias", (c_in,), "beta", 1.0),
+        (f"{path}/conv_in/weight", (c_out, c_in, 3, 3), "conv", 1.0), (f"{path}/conv_in/bias", (c_out,), "bias", 1.0),
+        (f"{path}/lin_embed/weight", (ted, c_out), "linear", 1.0), (f"{path}/lin_embed/bias", (c_out,), "bias", 1.0),
+        (f"{path}/norm_out/weight", (c_out,), "gamma", 1.0), (f"{path}/norm_out/bias", (c_out,), "beta", 1.0),
+        (f"{path}/conv_out/weight", (c_out, c_out, 3, 3), "conv", RESID_SCALE),
+        (f"{path}/conv_out/bias", (c_out,), "bias", 1.0),
+    ]
+    if c_in != c_out:
+        s += [(f"{path}/skip_connection/weight", (c_out, c_in, 1, 1), "conv", 1.0),
+              (f"{path}/skip_connection/bias", (c_out,), "bias", 1.0)]
+    return s
+
+
+def _st_specs(path: str, c: int, ctx: int, depth: int) -> List[Spec]:
+    s: List[Spec] = [
+        (f"{path}/norm/weight", (c,), "gamma", 1.0), (f"{path}/norm/bias", (c,), "beta", 1.0),
+        (f"{path}/proj_in/weight", (c, c), "linear", 1.0), (f"{path}/proj_in/bias", (c,), "bias", 1.0),
+        (f"{path}/proj_out/weight", (c, c), "linear", RESID_SCALE), (f"{path}/proj_out/bias", (c,), "bias", 1.0),
+    ]
+    for j in range(depth):
+        b = f"{path}/transformer_{j}"
+        for n in ("norm1", "norm2", "norm3"):
+            s += [(f"{b}/{n}/weight", (c,), "gamma", 1.0), (f"{b}/{n}/bias", (c,), "beta", 1.0)]
+        s += [
+            (f"{b}/attn1/query/weight", (c, c), "linear", 1.0), (f"{b}/attn1/key/weight", (c, c), "linear", 1.0),
+            (f"{b}/attn1/value/weight", (c, c), "linear", 1.0),
+            (f"{b}/attn1/out/weight", (c, c), "linear", RESID_SCALE), (f"{b}/attn1/out/bias", (c,), "bias", 1.0),
+            (f"{b}/attn2/query/weight", (c, c), "linear", 1.0), (f"{b}/attn2/key/weight", (ctx, c), "linear", 1.0),
+            (f"{b}/attn2/value/weight", (ctx, c), "linear", 1.0),
+            (f"{b}/attn2/out/weight", (c, c), "linear", RESID_SCALE), (f"{b}/attn2/out/bias", (c,), "bias", 1.0),
+            (f"{b}/mlp/geglu/proj/weight", (c, 8 * c), "linear", 1.0), (f"{b}/mlp/geglu/proj/bias", (8 * c,), "bias", 1.0),
+            (f"{b}/mlp/lin/weight", (4 * c, c), "linear", RESID_SCALE), (f"{b}/mlp/lin/bias", (c,), "bias", 1.0),
+        ]
+    return s
+
+
+def unet_tensor_specs(cfg: UNetConfig) -> List[Spec]:
+    mc, ted = cfg.model_channels, cfg.time_embed_dim
+    s: List[Spec] = [
+        ("lin1_time_embed/weight", (mc, ted), "linear", 1.0), ("lin1_time_embed/bias", (ted,), "bias", 1.0),
+        ("lin2_time_embed/weight", (ted, ted), "linear", 1.0), ("lin2_time_embed/bias", (ted,), "bias", 1.0),
+        ("lin1_label_embed/weight", (cfg.adm_in_channels, ted), "linear", 1.0), ("lin1_label_embed/bias", (ted,), "bias", 1.0),
+        ("lin2_label_embed/weight", (ted, ted), "linear", 1.0), ("lin2_label_embed/bias", (ted,), "bias", 1.0),
+    ]
+    ins, mid, outs = block_program(cfg)
+    for b in ins + outs:
+        if b.kind == "conv":
+            s += [(f"{b.path}/weight", (b.c_out, b.c_in, 3, 3), "conv", 1.0), (f"{b.path}/bias", (b.c_out,), "bias", 1.0)]
+        elif b.kind == "downsample":
+            s += [(f"{b.path}/weight", (b.c_out, b.c_in, 3, 3), "conv", 1.0), (f"{b.path}/bias", (b.c_out,), "bias", 1.0)]
+        elif b.kind == "resnet":
+            s += _res_specs(b.path, b.c_in, b.c_out, ted)
+        else:
+            s += _res_specs(f"{b.path}/res", b.c_in, b.c_out, ted)
+            if "transformer" in b.kind:
+                s += _st_specs(f"{b.path}/transformer", b.c_out, cfg.context_dim, b.depth)
+            if b.kind.endswith("upsample"):
+                s += [(f"{b.path}/upsample/conv/weight", (b.c_out, b.c_out, 3, 3), "conv", 1.0),
+                      (f"{b.path}/upsample/conv/bias", (b.c_out,), "bias", 1.0)]
+    s += _res_specs("middle_block/res1", mid.c_in, mid.c_out, ted)
+    s += _st_specs("middle_block/transformer", mid.c_out, cfg.context_dim, mid.depth)
+    s += _res_specs("middle_block/res2", mid.c_in, mid.c_out, ted)
+    s += [("norm_out/weight", (mc,), "gamma", 1.0), ("norm_out/bias", (mc,), "beta", 1.0),
+          ("conv_out/weight", (cfg.out_channels, mc, 3, 3), "conv", 1.0), ("conv_out/bias", (cfg.out_channels,), "bias", 1.0)]
+    return s
+
+
+def alphas_cumprod(n_steps: int = 1000) -> torch.Tensor:
+    """LegacyDDPMDiscretization: scaled-linear betas 0.00085 -> 0.012 (reference python/dump.py:29-36)."""
+    betas = np.linspace(0.00085 ** 0.5, 0.012 ** 0.5, n_steps, dtype=np.float64) ** 2
+    return torch.from_numpy(np.cumprod(1.0 - betas, axis=0)).to(torch.float16)
+
+
+def synth_weights(cfg: UNetConfig, seed: int = 0, device: str = "cpu") -> Dict[str, torch.Tensor]:
+    """Deterministic (per device type) synthetic f16 weights, reference layouts and names."""
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    out: Dict[str, torch.Tensor] = {}
+    for name, shape, kind, scale in unet_tensor_specs(cfg):
+        if kind == "linear":
+            t = torch.randn(shape, generator=gen, device=device) * (scale / shape[0] ** 0.5)
+        elif kind == "conv":
+            t = torch.randn(shape, generator=gen, device=device) * (scale / (shape[1] * shape[2] * shape[3]) ** 0.5)
+        elif kind == "bias":
+            t = torch.randn(shape, generator=gen, device=device) * 0.02
+        elif kind == "gamma":
+            t = 1.0 + torch.randn(shape, generator=gen, device=device) * 0.05
+        elif kind == "beta":
+            t = torch.randn(shape, generator=gen, device=device) * 0.05
+        else:
+            raise ValueError(kind)
+        out[name] = t.to(torch.float16)
+    out["alphas_cumprod"] = alphas_cumprod(cfg.n_steps).to(device)
+    return out
+
+
+def n_params(cfg: UNetConfig) -> int:
+    return sum(int(np.prod(s[1])) for s in unet_tensor_specs(cfg))
+
+
+_ENTRY = struct.Struct("<120sII4QQQ")
+_HEADER = struct.Struct("<8sIIQ")
+
+
+def build_pack(tensors: Dict[str, torch.Tensor], device: str | None = None, pin: bool = False) -> torch.Tensor:
+    """Serialises name->f16 tensor into one flat uint8 tensor (on `device`, default: the tensors' device)."""
+    items = list(tensors.items())
+    if device is None:
+        device = str(items[0][1].device)
+    table_bytes = _HEADER.size + _ENTRY.size * len(items)
+    off = (table_bytes + 255) // 256 * 256
+    data_offset = off
+    entries = []
+    for name, t in items:
+        if t.dtype != torch.float16:
+            raise TypeError(f"{name}: pack tensors must be f16")
+        if t.dim() > 4 or len(name.encode()) >= 120:
+            raise ValueError(f"{name}: unsupported rank/name")
+        nbytes = t.numel() * 2
+        shape = list(t.shape) + [0] * (4 - t.dim())
+        entries.append((name, t, off, nbytes, shape))
+        off = (off + nbytes + 255) // 256 * 256
+    total = off
+    if device == "cpu":
+        buf = torch.zeros(total, dtype=torch.uint8, pin_memory=pin)
+    else:
+        buf = torch.zeros(total, dtype=torch.uint8, device=device)
+    head = bytearray(_HEADER.pack(b"SDXLPK01", len(items), 0, data_offset))
+    for name, t, o, nbytes, shape in entries:
+        head += _ENTRY.pack(name.encode(), 0, t.dim(), *shape, o, nbytes)
+    buf[: len(head)] = torch.frombuffer(head, dtype=torch.uint8).to(buf.device)
+    for name, t, o, nbytes, shape in entries:
+        buf[o:o + nbytes] = t.contiguous().view(torch.uint8).reshape(-1).to(buf.device)
+    return buf
