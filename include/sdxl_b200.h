@@ -145,6 +145,12 @@ SDXL_API double sdxl_unet_alpha(const sdxl_unet* unet, int i);
  * the launch plan currently built for this UNet (0 before the first forward). */
 SDXL_API double sdxl_unet_plan_flops(const sdxl_unet* unet);
 SDXL_API int sdxl_unet_plan_num_ops(const sdxl_unet* unet);
+/* Device time of ONE execution of the current launch plan, summed per kernel kind and measured with CUDA
+ * events on the ctx stream (eager launches). Kind index: 0 implicit-GEMM (tcgen05), 1 attention, 2 GroupNorm,
+ * 3 LayerNorm, 4 GEMV, 5 timestep-embedding, 6 first conv, 7 upsample copy, 8 phase-split copy, 9 f32->f16 cast.
+ * All three arrays hold 16 entries (host). Used by bench.py for the per-kernel roofline. */
+SDXL_API int sdxl_unet_profile_plan(sdxl_unet* unet, double* ms_by_kind_host, double* flops_by_kind_host,
+                                    int* launches_by_kind_host);
 /* seeded N(0,1) exactly as the sampler generates it (device out). */
 SDXL_API int sdxl_randn(sdxl_ctx* ctx, float* out, size_t n, uint64_t seed, uint64_t subsequence);
 

@@ -613,6 +613,7 @@ extern "C" int sdxl_unet_load(sdxl_ctx* c, const sdxl_unet_cfg* cfg, const void*
 enum OpKind { OP_IGEMM, OP_ATTN, OP_GN, OP_LN, OP_GEMV, OP_TEMB, OP_CONV_IN, OP_UPS, OP_PHASE, OP_CAST16 };
 struct Op {
   OpKind kind;
+  double flops = 0;  // algorithmic FLOPs of this launch (igemm / attention), 0 for HBM-bound ops
   IgemmParams ig;
   AttnParams at;
   GnParams gn;
@@ -663,6 +664,11 @@ struct PlanBuilder {
     if (!p && !err) err = fail(c, 5001, "plan arena exhausted");
     return p;
   }
+  void add_flops(double f) {  // attribute to the op just pushed
+    if (err || P->ops.empty()) return;
+    P->ops.back().flops += f;
+    P->flops += f;
+  }
   // generic igemm op; segs reference view a0 (map 0) / a1 (map 1)
   void igemm(const ActView& a0, const ActView* a1, const std::vector<IgemmSeg>& segs, const __half* W, int N, int Ktot,
              int outH, int outW, int outB, int mode, int geglu_bn, void* out, int out_f32, int ldo, const float* bias,
@@ -696,7 +702,7 @@ struct PlanBuilder {
     ActView a{x, 1, 1, M, L.K};
     std::vector<IgemmSeg> segs{{0, 0, 0, 0, L.Kpad / 64}};
     igemm(a, nullptr, segs, L.w, L.N, L.Kpad, 1, M, 1, mode, L.geglu_bn, out, out_f32, ldo, L.b, 0, res, ldr);
-    P->flops += 2.0 * M * (double)L.K * L.N;
+    add_flops(2.0 * M * (double)L.K * L.N);
   }
   // 3x3 stride-1 conv (+ optional fused 1x1 skip segment on a1)
   void conv3(const ActView& a, const ActView* skip, const Conv& cv, float* out, const float* bias, int bias_bstride,
@@ -706,7 +712,7 @@ struct PlanBuilder {
       for (int kw = 0; kw < 3; ++kw) segs.push_back({0, (int16_t)(kw - 1), (int16_t)(kh - 1), 0, cv.Ipad / 64});
     if (skip) segs.push_back({1, 0, 0, 0, cv.I2pad / 64});
     igemm(a, skip, segs, cv.w, cv.O, cv.Ktot, a.H, a.W, a.Bn, IGEMM_LINEAR, 0, out, 1, cv.O, bias, bias_bstride, res, cv.O);
-    P->flops += 2.0 * a.Bn * a.H * a.W * (double)cv.O * (9.0 * cv.I + cv.I2);
+    add_flops(2.0 * a.Bn * a.H * a.W * (double)cv.O * (9.0 * cv.I + cv.I2));
   }
   void gn(const float* x1, int C1, const float* x2, int C2, int HW, const Norm& n, int silu, __half* y, __half* raw) {
     if (err) return;
@@ -809,7 +815,7 @@ struct PlanBuilder {
       if (r) { err = fail(c, r, "tensor map creation failed (attention)"); return; }
     }
     P->ops.push_back(op);
-    P->flops += 4.0 * Bf * T * (double)S * (n_head * 64);
+    add_flops(4.0 * Bf * T * (double)S * (n_head * 64));
   }
 };
 
@@ -939,7 +945,7 @@ static int build_plan_ops(sdxl_unet* u, Plan* P, Arena* A) {
         }
       float* y = B.buf<float>((size_t)Bf * H2 * W2 * Cx);
       B.igemm(a, nullptr, segs, b.conv.w, b.conv.O, b.conv.Ktot, H2, W2, Bf, IGEMM_LINEAR, 0, y, 1, b.conv.O, b.conv.b, 0, nullptr, 0);
-      P->flops += 2.0 * Bf * H2 * W2 * 9.0 * Cx * b.conv.O;
+      B.add_flops(2.0 * Bf * H2 * W2 * 9.0 * Cx * b.conv.O);
       x = y; H = H2; W = W2;
     }
     saved.push_back({x, Cx, H, W});
@@ -982,7 +988,7 @@ static int build_plan_ops(sdxl_unet* u, Plan* P, Arena* A) {
       for (int kw = 0; kw < 3; ++kw) segs.push_back({0, (int16_t)(kw - 1), (int16_t)(kh - 1), 0, u->conv_out.Ipad / 64});
     B.igemm(a, nullptr, segs, u->conv_out.w, u->conv_out.O, u->conv_out.Ktot, H, W, Bf, IGEMM_LINEAR, 0, P->eps, 1, P->eps_ld,
             u->conv_out.b, 0, nullptr, 0);
-    P->flops += 2.0 * Bf * H * W * 9.0 * Cx * u->conv_out.O;
+    B.add_flops(2.0 * Bf * H * W * 9.0 * Cx * u->conv_out.O);
   }
   return B.err;
 }
@@ -1158,6 +1164,36 @@ extern "C" int sdxl_unet_forward_f32(sdxl_unet* u, int B, int h, int w, const fl
   if ((r = run_plan(u))) return r;
   KL(c, nhwc_to_nchw_f32_launch(c->stream, P->eps, B, h * w, u->cfg.out_channels, P->eps_ld, eps_out));
   return 0;
+}
+// Per-kernel-kind device time of one plan execution, measured with CUDA events on the ctx stream
+// (eager launches, one event pair per op). kinds: see OpKind. Arrays must hold 16 entries.
+extern "C" int sdxl_unet_profile_plan(sdxl_unet* u, double* ms_by_kind, double* flops_by_kind, int* launches_by_kind) {
+  if (!u || !u->plan) return -1;
+  sdxl_ctx* c = u->ctx;
+  Plan* P = u->plan.get();
+  const size_t n = P->ops.size();
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) CU(c, cudaEventCreate(&e));
+  int r = 0;
+  CU(c, cudaEventRecord(ev[0], c->stream));
+  for (size_t i = 0; i < n && !r; ++i) {
+    r = exec_op(c, P->ops[i]);
+    if (!r && cudaEventRecord(ev[i + 1], c->stream) != cudaSuccess) r = -2;
+  }
+  cudaError_t se = cudaStreamSynchronize(c->stream);
+  for (int k = 0; k < 16; ++k) { ms_by_kind[k] = 0; flops_by_kind[k] = 0; launches_by_kind[k] = 0; }
+  if (!r && se == cudaSuccess)
+    for (size_t i = 0; i < n; ++i) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+      const int k = (int)P->ops[i].kind;
+      ms_by_kind[k] += ms;
+      flops_by_kind[k] += P->ops[i].flops;
+      launches_by_kind[k] += (P->ops[i].kind == OP_GN) ? 2 : 1;
+    }
+  for (auto& e : ev) cudaEventDestroy(e);
+  if (se != cudaSuccess) return fail(c, (int)se, "profile run failed: %s", cudaGetErrorString(se));
+  return r;
 }
 extern "C" double sdxl_unet_alpha(const sdxl_unet* u, int i) {
   if (!u || i < 0 || i >= (int)u->alphas.size()) return NAN;

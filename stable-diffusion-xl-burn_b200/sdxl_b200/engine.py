@@ -301,6 +301,15 @@ class Diffuser:
     def plan_num_ops(self) -> int:
         return int(self.ctx.lib.sdxl_unet_plan_num_ops(self.h))
 
+    KIND_NAMES = ["igemm_tcgen05", "attention_tcgen05", "group_norm", "layer_norm", "gemv", "timestep_embedding",
+                  "conv_in", "upsample2x", "phase_split", "cast_f16"]
+
+    def profile_plan(self) -> Dict[str, Dict[str, float]]:
+        """Per-kernel-kind device time (ms), algorithmic FLOPs and launch count of one plan execution."""
+        ms, fl, ln = (C.c_double * 16)(), (C.c_double * 16)(), (C.c_int * 16)()
+        self.ctx.check(self.ctx.lib.sdxl_unet_profile_plan(self.h, ms, fl, ln), "sdxl_unet_profile_plan")
+        return {n: {"ms": ms[i], "flops": fl[i], "launches": ln[i]} for i, n in enumerate(self.KIND_NAMES) if ln[i]}
+
     def alpha(self, i: int) -> float:
         return float(self.ctx.lib.sdxl_unet_alpha(self.h, i))
 

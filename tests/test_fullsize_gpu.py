@@ -1,0 +1,67 @@
+"""Full-size (SDXL base, 2.57 B parameters) GPU checks through the C ABI.
+
+ * 256x256 (BASELINE.json configs[0] shape): one forward against the CPU f32 oracle on the same synthetic
+   weights — the largest case the oracle finishes in seconds.
+ * 1024x1024 (configs[1]): size-independent properties — determinism, batch independence (the CFG-batched
+   forward equals two bs=1 forwards, which is how the reference runs them, stablediffusion/mod.rs:523-537),
+   finiteness, and the plan's algorithmic FLOP count against SURVEY 8(d).
+"""
+import pytest
+import torch
+
+import sdxl_b200
+from sdxl_b200 import SDXL_BASE, Diffuser
+from oracle import unet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+@pytest.fixture(scope="module")
+def base(ctx):
+    w = sdxl_b200.synth_weights(SDXL_BASE, seed=0, device=str(ctx.device))
+    d = Diffuser(ctx, SDXL_BASE, sdxl_b200.build_pack(w))
+    yield d, w
+    d.close()
+
+
+def _inputs(B, hw, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, 4, hw, hw, generator=g)
+    ctx_t = torch.randn(B, 77, 2048, generator=g).half().float()
+    y = torch.randn(B, 2816, generator=g).half().float()
+    return x, ctx_t, y
+
+
+def test_base_256_forward_vs_oracle(base):
+    d, w = base
+    x, ctx_t, y = _inputs(1, 32)
+    out = d.unet_forward(x, [749], ctx_t, y)
+    wf = O.to_f32(w)
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    ref = O.unet_forward(SDXL_BASE, wf, x, torch.tensor([749]), ctx_t, y)
+    e = rel_err(out, ref)
+    print(f"base 256x256 forward rel err vs oracle: {e:.3e}")
+    assert torch.isfinite(out).all() and e < 2e-3
+
+
+def test_base_1024_properties(base):
+    d, _ = base
+    x, ctx_t, y = _inputs(2, 128, seed=1)
+    x[1] = x[0]  # CFG batching: same latent, two conditionings
+    out2 = d.unet_forward(x, [999], ctx_t, y)
+    assert torch.isfinite(out2).all() and out2.shape == (2, 4, 128, 128)
+    fl = d.plan_flops
+    print(f"plan FLOPs B=2 1024^2: {fl:.6e} ({d.plan_num_ops} ops)")
+    assert abs(fl / (2 * 6.7612e12) - 1) < 2e-4  # 6.7612 TFLOP per forward
+    again = d.unet_forward(x, [999])
+    assert torch.equal(out2, again)  # deterministic: no atomics on the path
+    a = d.unet_forward(x[:1], [999], ctx_t[:1], y[:1])
+    b = d.unet_forward(x[1:], [999], ctx_t[1:], y[1:])
+    e = max(rel_err(a, out2[:1]), rel_err(b, out2[1:]))
+    print(f"batched vs two bs=1 forwards: rel err {e:.3e}")
+    assert e < 2e-5  # only GroupNorm partial-sum chunking depends on the batch size
