@@ -133,9 +133,9 @@ int gn_launch(cudaStream_t st, GnParams& p) {
   int R = 384 / V;
   if (R < 1) R = 1;
   if (R > 8) R = 8;
-  int nchunk = 296 / (p.B > 0 ? p.B : 1);
-  if (nchunk < 1) nchunk = 1;
-  if (nchunk > kGnMaxChunk) nchunk = kGnMaxChunk;
+  // chunking depends on HW only (never on the batch size): every sample's statistics are summed in the
+  // same order whatever B is, which keeps the whole forward batch-invariant bit for bit.
+  int nchunk = 148;
   const int max_chunks = cdiv(p.HW, R);
   if (nchunk > max_chunks) nchunk = max_chunks;
   p.nchunk = nchunk;

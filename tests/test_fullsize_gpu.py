@@ -64,4 +64,6 @@ def test_base_1024_properties(base):
     b = d.unet_forward(x[1:], [999], ctx_t[1:], y[1:])
     e = max(rel_err(a, out2[:1]), rel_err(b, out2[1:]))
     print(f"batched vs two bs=1 forwards: rel err {e:.3e}")
-    assert e < 2e-5  # only GroupNorm partial-sum chunking depends on the batch size
+    # every kernel sums each sample in an order that does not depend on the batch size (tile shapes only change
+    # which CTA owns an output), so the CFG-batched forward is bit-identical to the reference's two bs=1 forwards
+    assert torch.equal(a, out2[:1]) and torch.equal(b, out2[1:])
