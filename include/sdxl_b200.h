@@ -151,6 +151,8 @@ SDXL_API int sdxl_unet_plan_num_ops(const sdxl_unet* unet);
  * All three arrays hold 16 entries (host). Used by bench.py for the per-kernel roofline. */
 SDXL_API int sdxl_unet_profile_plan(sdxl_unet* unet, double* ms_by_kind_host, double* flops_by_kind_host,
                                     int* launches_by_kind_host);
+/* Same measurement, one CSV row per launch (analysis aid; written to `path_host`). */
+SDXL_API int sdxl_unet_profile_dump(sdxl_unet* unet, const char* path_host);
 /* seeded N(0,1) exactly as the sampler generates it (device out). */
 SDXL_API int sdxl_randn(sdxl_ctx* ctx, float* out, size_t n, uint64_t seed, uint64_t subsequence);
 

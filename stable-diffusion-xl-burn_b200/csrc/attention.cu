@@ -1,42 +1,52 @@
 // Fused multi-head attention for the UNet's SpatialTransformer blocks (head dim 64, no mask):
 //   out = softmax(q k^T / sqrt(64)) v            (reference src/backend.rs:4-19,32-79,88-128;
 //                                                 called from unet/mod.rs:1013-1019)
-// Flash-style: one CTA owns 128 queries of one head and streams 128-key blocks. Both contractions run
-// on tcgen05 tensor cores with accumulators in TMEM:
-//   S = Q K^T   : A = Q tile (K-major, TMA SW128), B = K tile (K-major)           -> TMEM cols [0,128)
-//   O_j = P V   : A = P (f16, written by the softmax warps into SW128 smem),
-//                 B = V tile (MN-major: keys are the contraction dim)              -> TMEM cols [128,192)
-// Online softmax (running max / sum, f32) lives in registers of 128 threads (one query row each);
-// the running output is rescaled in registers, so TMEM never needs a read-modify-write.
-// Warp roles (192 threads): warp0 TMA producer, warp1 MMA issuer + TMEM owner, warps 2..5 softmax.
+// Flash-style on tcgen05 tensor cores with TMEM accumulators. One CTA owns TWO 128-query tiles (A, B) of one
+// head and streams 128-key blocks once for both; two softmax warpgroups ping-pong against one MMA issuer, so
+// the tensor pipe works on tile B while tile A is in the exp/rescale phase and vice versa:
+//   S_x = Q_x K^T : A = Q tile (K-major, TMA SW128), B = K tile (K-major)            -> TMEM S_A / S_B (128 cols each)
+//   O_x,j = P_x V : A = P_x (f16, written by softmax group x into SW128 smem),
+//                   B = V tile (MN-major: keys are the contraction dim)               -> TMEM O_x[j&1] (64 cols each)
+// Online softmax (running max / sum, f32) lives in registers of 128 threads per tile (one query row each). The
+// per-block P V result is double-buffered in TMEM and folded into the register accumulator one block late, so
+// the softmax warps never wait for the tensor pipe in steady state and TMEM never needs a read-modify-write.
+// Warp roles (320 threads): warp0 TMA producer, warp1 MMA issuer + TMEM owner, warps 2..5 softmax A, 6..9 softmax B.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace sdxl {
 
-static constexpr int kQBytes = 128 * 128;       // 128 rows x 64 halves
-static constexpr int kKVBytes = 128 * 128;
-static constexpr int kPBytes = 2 * 128 * 128;   // 128 rows x 128 keys, two 64-key swizzle panels
-static constexpr int kAttnSmem = kQBytes + 4 * kKVBytes + kPBytes + 128;
+static constexpr int kTileBytes = 128 * 128;        // 128 rows x 64 halves (Q, K or V tile)
+static constexpr int kPBytes = 2 * 128 * 128;       // 128 rows x 128 keys, two 64-key swizzle panels
+static constexpr int kAttnSmem = 2 * kTileBytes + 4 * kTileBytes + 2 * kPBytes + 256;
+static constexpr int kAttnThreads = 320;
 
-__global__ void __launch_bounds__(192, 2) attention_kernel(const __grid_constant__ AttnParams p) {
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + kQBytes;            // 2 stages
-  uint8_t* sV = sK + 2 * kKVBytes;       // 2 stages
-  uint8_t* sP = sV + 2 * kKVBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kPBytes);
+  uint8_t* sQ = smem;                       // [2] tiles A, B
+  uint8_t* sK = sQ + 2 * kTileBytes;        // [2] stages
+  uint8_t* sV = sK + 2 * kTileBytes;        // [2] stages
+  uint8_t* sP = sV + 2 * kTileBytes;        // [2] groups
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kPBytes);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;   // [2]
-  uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* pv_done = bars + 7;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* kv_full = bars + 1;    // [2]
+  uint64_t* kv_empty = bars + 3;   // [2]
+  uint64_t* s_full = bars + 5;     // [2] per group
+  uint64_t* p_full = bars + 7;     // [2] per group, 128 arrivals
+  uint64_t* pv_done = bars + 9;    // [2] per group
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
   const int nblk = (p.S + 127) / 128;
+  const int row0 = qt * 256;
+  const bool hasB = row0 + 128 < p.T;   // second tile holds at least one valid query
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) {
@@ -47,33 +57,34 @@ __global__ void __launch_bounds__(192, 2) attention_kernel(const __grid_constant
     tma_prefetch_desc(&p.tmK);
     tma_prefetch_desc(&p.tmV);
     mbar_init(q_full, 1);
-    mbar_init(&kv_full[0], 1);
-    mbar_init(&kv_full[1], 1);
-    mbar_init(&kv_empty[0], 1);
-    mbar_init(&kv_empty[1], 1);
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
-    mbar_init(pv_done, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&pv_done[i], 1);
+    }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr, 256);
+  if (warp == 1) tmem_alloc(tmem_ptr, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t tmem_S = tmem_base;
-  const uint32_t tmem_O = tmem_base + 128;
+  griddep_wait();  // PDL: the prologue above overlapped the previous kernel's tail
+  griddep_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(q_full, kQBytes);
-      tma_load_3d(sQ, &p.tmQ, q_full, p.q_col0 + head * 64, qt * 128, b);
+      mbar_expect_tx(q_full, (hasB ? 2 : 1) * kTileBytes);
+      tma_load_3d(sQ, &p.tmQ, q_full, p.q_col0 + head * 64, row0, b);
+      if (hasB) tma_load_3d(sQ + kTileBytes, &p.tmQ, q_full, p.q_col0 + head * 64, row0 + 128, b);
       for (int j = 0; j < nblk; ++j) {
         const int stage = j & 1;
         mbar_wait(&kv_empty[stage], ((j >> 1) & 1) ^ 1);
-        mbar_expect_tx(&kv_full[stage], 2 * kKVBytes);
-        tma_load_3d(sK + stage * kKVBytes, &p.tmK, &kv_full[stage], p.k_col0 + head * 64, j * 128, b);
-        tma_load_3d(sV + stage * kKVBytes, &p.tmV, &kv_full[stage], p.v_col0 + head * 64, j * 128, b);
+        mbar_expect_tx(&kv_full[stage], 2 * kTileBytes);
+        tma_load_3d(sK + stage * kTileBytes, &p.tmK, &kv_full[stage], p.k_col0 + head * 64, j * 128, b);
+        tma_load_3d(sV + stage * kTileBytes, &p.tmV, &kv_full[stage], p.v_col0 + head * 64, j * 128, b);
       }
     }
   } else if (warp == 1) {
@@ -81,124 +92,166 @@ __global__ void __launch_bounds__(192, 2) attention_kernel(const __grid_constant
       const uint32_t idesc_qk = make_idesc_f16(128, false);
       const uint32_t idesc_pv = make_idesc_f16(64, true);
       const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
+      // S_x = Q_x K_j^T
+      auto issue_qk = [&](int x, int stage) {
+        const uint32_t qa = q_addr + x * kTileBytes, ka = smem_u32(sK + stage * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_f16(tmem_base + x * 128, make_sw128_desc(qa + k * 32), make_sw128_desc(ka + k * 32), idesc_qk, k > 0);
+        tc_commit(&s_full[x]);
+      };
+      // O_x[j&1] = P_x V_j
+      auto issue_pv = [&](int x, int j) {
+        const uint32_t pa = p_addr + x * kPBytes, va = smem_u32(sV + (j & 1) * kTileBytes);
+        const uint32_t d = tmem_base + 256 + x * 128 + (j & 1) * 64;
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+          tc_mma_f16(d, make_sw128_desc(pa + (t >> 2) * (128 * 128) + (t & 3) * 32), make_sw128_desc(va + t * 2048), idesc_pv,
+                     t > 0);
+        tc_commit(&pv_done[x]);
+      };
       mbar_wait(q_full, 0);
       mbar_wait(&kv_full[0], 0);
       tc_fence_after();
-      {
-        const uint32_t k_addr = smem_u32(sK);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          tc_mma_f16(tmem_S, make_sw128_desc(q_addr + k * 32), make_sw128_desc(k_addr + k * 32), idesc_qk, k > 0);
-        tc_commit(s_full);
-      }
+      issue_qk(0, 0);
+      if (hasB) issue_qk(1, 0);
       for (int j = 0; j < nblk; ++j) {
-        const int stage = j & 1;
-        // P(j) written and S(j) fully consumed by the softmax warps
-        mbar_wait(p_full, j & 1);
+        const bool more = j + 1 < nblk;
+        mbar_wait(&p_full[0], j & 1);  // P_A(j) written, S_A(j) consumed
         tc_fence_after();
-        const uint32_t v_addr = smem_u32(sV + stage * kKVBytes);
-#pragma unroll
-        for (int t = 0; t < 8; ++t)
-          tc_mma_f16(tmem_O, make_sw128_desc(p_addr + (t >> 2) * (128 * 128) + (t & 3) * 32),
-                     make_sw128_desc(v_addr + t * 2048), idesc_pv, t > 0);
-        tc_commit(pv_done);
-        tc_commit(&kv_empty[stage]);
-        if (j + 1 < nblk) {
-          const int ns = (j + 1) & 1;
-          mbar_wait(&kv_full[ns], ((j + 1) >> 1) & 1);
+        issue_pv(0, j);
+        if (more) {
+          mbar_wait(&kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
           tc_fence_after();
-          const uint32_t k_addr = smem_u32(sK + ns * kKVBytes);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc_mma_f16(tmem_S, make_sw128_desc(q_addr + k * 32), make_sw128_desc(k_addr + k * 32), idesc_qk, k > 0);
-          tc_commit(s_full);
+          issue_qk(0, (j + 1) & 1);
         }
+        if (hasB) {
+          mbar_wait(&p_full[1], j & 1);
+          tc_fence_after();
+          issue_pv(1, j);
+        }
+        tc_commit(&kv_empty[j & 1]);  // K_j / V_j no longer needed once everything issued so far retires
+        if (more && hasB) issue_qk(1, (j + 1) & 1);
       }
     }
   } else {
-    const int q = warp & 3;
-    const int r = q * 32 + lane;  // query row in tile == TMEM lane
-    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    const float sl2e = p.scale_log2e;
-    float m = -INFINITY, l = 0.f;
-    float O[64];
+    const int x = (warp - 2) >> 2;  // softmax group: 0 = tile A, 1 = tile B
+    if (x == 0 || hasB) {
+      const int q = warp & 3;
+      const int r = q * 32 + lane;  // query row in tile == TMEM lane
+      const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+      const uint32_t tS = tmem_base + lane_off + x * 128;
+      const uint32_t tO = tmem_base + lane_off + 256 + x * 128;
+      const float sl2e = p.scale_log2e;
+      float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
+      float O[64];
 #pragma unroll
-    for (int i = 0; i < 64; ++i) O[i] = 0.f;
-    uint8_t* prow = sP + (r >> 3) * 1024 + (r & 7) * 128;
-    const int rx = r & 7;
+      for (int i = 0; i < 64; ++i) O[i] = 0.f;
+      uint8_t* prow = sP + x * kPBytes + (r >> 3) * 1024 + (r & 7) * 128;
+      const int rx = r & 7;
 
-    for (int j = 0; j < nblk; ++j) {
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-      const int kbase = j * 128;
-      // pass 1: row max over valid keys
-      float mx = -INFINITY;
+      for (int j = 0; j < nblk; ++j) {
+        mbar_wait(&s_full[x], j & 1);
+        // P V of block j-1 was issued before Q K^T of block j, so it has retired too. Observe its phase NOW,
+        // before this thread's p_full arrival lets the MMA warp issue P V of block j (a waiter must never
+        // fall two phases behind an mbarrier).
+        if (j > 0) mbar_wait(&pv_done[x], (j - 1) & 1);
+        tc_fence_after();
+        const int kbase = j * 128;
+        const bool ragged = kbase + 128 > p.S;
+        // pass 1: row max over valid keys
+        float mx = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < 128; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_off + c, v);
-        tmem_ld_wait();
+        for (int c = 0; c < 128; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(tS + c, v);
+          tmem_ld_wait();
+          if (!ragged) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (kbase + c + i < p.S) mx = fmaxf(mx, __uint_as_float(v[i]));
-      }
-      const float m_new = fmaxf(m, mx);
-      const float alpha = exp2f((m - m_new) * sl2e);
-      const float mb = m_new * sl2e;
-      float sum = 0.f;
-      // pass 2: p = exp2(s*scale - m*scale) -> f16 -> swizzled smem (A operand of the PV MMA)
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (kbase + c + i < p.S) mx = fmaxf(mx, __uint_as_float(v[i]));
+          }
+        }
+        const float m_new = fmaxf(m, mx);
+        const float alpha = ex2_approx((m - m_new) * sl2e);
+        const float mb = m_new * sl2e;
+        float sum = 0.f;
+        // pass 2: p = exp2(s*scale - m*scale) -> f16 -> swizzled smem (A operand of the PV MMA)
 #pragma unroll 1
-      for (int c = 0; c < 128; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_off + c, v);
-        tmem_ld_wait();
-        uint32_t h[16];
+        for (int c = 0; c < 128; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(tS + c, v);
+          tmem_ld_wait();
+          uint32_t h[16];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = (kbase + c + i < p.S) ? exp2f(fmaf(__uint_as_float(v[i]), sl2e, -mb)) : 0.f;
-          float p1 = (kbase + c + i + 1 < p.S) ? exp2f(fmaf(__uint_as_float(v[i + 1]), sl2e, -mb)) : 0.f;
-          __half2 t = __floats2half2_rn(p0, p1);
-          const float2 back = __half22float2(t);  // sum exactly what the tensor core will see
-          sum += back.x + back.y;
-          h[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
+          for (int i = 0; i < 32; i += 2) {
+            float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sl2e, -mb));
+            float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sl2e, -mb));
+            if (ragged) {
+              if (kbase + c + i >= p.S) p0 = 0.f;
+              if (kbase + c + i + 1 >= p.S) p1 = 0.f;
+            }
+            sum += p0 + p1;
+            __half2 t = __floats2half2_rn(p0, p1);
+            h[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
+          }
+          uint8_t* panel = prow + (c >> 6) * (128 * 128);
+          const int ch0 = (c & 63) >> 3;  // first 16B chunk of this 32-key group inside the 128B row
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            *reinterpret_cast<uint4*>(panel + (((ch0 + u) ^ rx) << 4)) =
+                make_uint4(h[4 * u], h[4 * u + 1], h[4 * u + 2], h[4 * u + 3]);
         }
-        uint8_t* panel = prow + (c >> 6) * (128 * 128);
-        const int ch0 = (c & 63) >> 3;  // first 16B chunk of this 32-key group inside the 128B row
+        l = l * alpha + sum;
+        m = m_new;
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(&p_full[x]);
+        // fold in the PREVIOUS block's P V (already complete: it was issued before this block's Q K^T)
+        if (j > 0) {
+          const uint32_t to = tO + ((j - 1) & 1) * 64;
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          *reinterpret_cast<uint4*>(panel + (((ch0 + u) ^ rx) << 4)) =
-              make_uint4(h[4 * u], h[4 * u + 1], h[4 * u + 2], h[4 * u + 3]);
-      }
-      l = l * alpha + sum;
-      m = m_new;
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(p_full);
-      // accumulate this block's P V
-      mbar_wait(pv_done, j & 1);
-      tc_fence_after();
+          for (int c = 0; c < 64; c += 32) {
+            uint32_t v[32];
+            tmem_ld32(to + c, v);
+            tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 64; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_O + lane_off + c, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) O[c + i] = fmaf(O[c + i], alpha, __uint_as_float(v[i]));
-      }
-    }
-    const int t = qt * 128 + r;
-    if (t < p.T) {
-      const float inv = 1.0f / l;
-      __half* o = p.out + ((size_t)b * p.T + t) * p.ldo + head * 64;
-#pragma unroll
-      for (int c = 0; c < 64; c += 8) {
-        uint32_t h[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          __half2 t2 = __floats2half2_rn(O[c + 2 * i] * inv, O[c + 2 * i + 1] * inv);
-          h[i] = *reinterpret_cast<uint32_t*>(&t2);
+            for (int i = 0; i < 32; ++i) O[c + i] = fmaf(O[c + i], alpha_prev, __uint_as_float(v[i]));
+          }
         }
-        *reinterpret_cast<uint4*>(o + c) = make_uint4(h[0], h[1], h[2], h[3]);
+        alpha_prev = alpha;
+      }
+      {
+        const int j = nblk - 1;
+        mbar_wait(&pv_done[x], j & 1);
+        tc_fence_after();
+        const uint32_t to = tO + (j & 1) * 64;
+#pragma unroll
+        for (int c = 0; c < 64; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(to + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) O[c + i] = fmaf(O[c + i], alpha_prev, __uint_as_float(v[i]));
+        }
+      }
+      const int t = row0 + x * 128 + r;
+      if (t < p.T) {
+        const float inv = 1.0f / l;
+        __half* o = p.out + ((size_t)b * p.T + t) * p.ldo + head * 64;
+#pragma unroll
+        for (int c = 0; c < 64; c += 8) {
+          uint32_t h[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            __half2 t2 = __floats2half2_rn(O[c + 2 * i] * inv, O[c + 2 * i + 1] * inv);
+            h[i] = *reinterpret_cast<uint32_t*>(&t2);
+          }
+          *reinterpret_cast<uint4*>(o + c) = make_uint4(h[0], h[1], h[2], h[3]);
+        }
       }
     }
   }
@@ -207,7 +260,7 @@ __global__ void __launch_bounds__(192, 2) attention_kernel(const __grid_constant
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -218,9 +271,8 @@ int attention_launch(cudaStream_t st, const AttnParams& p) {
     if (e != cudaSuccess) return (int)e;
     attr = true;
   }
-  dim3 grid((p.T + 127) / 128, p.n_head, p.B);
-  attention_kernel<<<grid, 192, kAttnSmem, st>>>(p);
-  return (int)cudaGetLastError();
+  dim3 grid((p.T + 255) / 256, p.n_head, p.B);
+  return launch_kernel(attention_kernel, grid, dim3(kAttnThreads), (size_t)kAttnSmem, st, true, p);
 }
 
 }  // namespace sdxl

@@ -35,6 +35,14 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   return t;
 }
 
+// Programmatic dependent launch (PDL). wait: block until the preceding kernel in the stream has completed
+// and its memory is visible (no-op when the kernel was launched without the PDL attribute).
+// launch_dependents: allow the next kernel's CTAs to start their prologue as SM resources free up.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------

@@ -4,9 +4,16 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <stdlib.h>
+
 namespace sdxl {
 
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+
+bool pdl_enabled() {
+  static const bool on = getenv("SDXL_B200_NO_PDL") == nullptr;
+  return on;
+}
 
 // ------------------------------------------------------------------------------------------------
 // GEMV: one warp per output column, up to 8 batch rows accumulated together.
@@ -220,6 +227,8 @@ int phase_split_launch(cudaStream_t st, const float* x, int B, int H, int W, int
 }
 
 __global__ void cast_f32_f16_kernel(const float* __restrict__ x, size_t n, __half* __restrict__ y) {
+  griddep_wait();
+  griddep_launch_dependents();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     y[i] = __float2half_rn(x[i]);
 }
@@ -231,8 +240,7 @@ int cast_f32_to_f16_launch(cudaStream_t st, const float* x, size_t n, __half* y)
   int grid = cdiv((long)n, 256);
   if (grid > 148 * 16) grid = 148 * 16;
   if (grid < 1) grid = 1;
-  cast_f32_f16_kernel<<<grid, 256, 0, st>>>(x, n, y);
-  return (int)cudaGetLastError();
+  return launch_kernel(cast_f32_f16_kernel, dim3(grid), dim3(256), (size_t)0, st, true, x, n, y);
 }
 int cast_f16_to_f32_launch(cudaStream_t st, const __half* x, size_t n, float* y) {
   int grid = cdiv((long)n, 256);

@@ -1195,6 +1195,46 @@ extern "C" int sdxl_unet_profile_plan(sdxl_unet* u, double* ms_by_kind, double* 
   if (se != cudaSuccess) return fail(c, (int)se, "profile run failed: %s", cudaGetErrorString(se));
   return r;
 }
+// Per-op dump of one eager plan execution (CUDA-event time per launch) as CSV: analysis aid for profiles/.
+extern "C" int sdxl_unet_profile_dump(sdxl_unet* u, const char* path) {
+  if (!u || !u->plan || !path) return -1;
+  sdxl_ctx* c = u->ctx;
+  Plan* P = u->plan.get();
+  const size_t n = P->ops.size();
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) CU(c, cudaEventCreate(&e));
+  int r = 0;
+  CU(c, cudaEventRecord(ev[0], c->stream));
+  for (size_t i = 0; i < n && !r; ++i) {
+    r = exec_op(c, P->ops[i]);
+    if (!r && cudaEventRecord(ev[i + 1], c->stream) != cudaSuccess) r = -2;
+  }
+  cudaError_t se = cudaStreamSynchronize(c->stream);
+  if (!r && se == cudaSuccess) {
+    FILE* f = fopen(path, "w");
+    if (!f) r = fail(c, -3, "cannot open %s", path);
+    else {
+      fprintf(f, "op,kind,us,gflop,tflops,M_tiles,N,BN,Kblocks,T,S,heads\n");
+      static const char* names[] = {"igemm", "attention", "group_norm", "layer_norm", "gemv", "temb", "conv_in", "upsample", "phase_split", "cast16"};
+      for (size_t i = 0; i < n; ++i) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+        const Op& o = P->ops[i];
+        int mt = 0, N = 0, BN = 0, kb = 0, T = 0, S = 0, H = 0;
+        if (o.kind == OP_IGEMM) {
+          mt = o.ig.tilesW * o.ig.tilesH * o.ig.tilesB; N = o.ig.N; BN = o.ig.BN;
+          for (int s2 = 0; s2 < o.ig.nseg; ++s2) kb += o.ig.seg[s2].nkb;
+        } else if (o.kind == OP_ATTN) { T = o.at.T; S = o.at.S; H = o.at.n_head; }
+        fprintf(f, "%zu,%s,%.2f,%.3f,%.1f,%d,%d,%d,%d,%d,%d,%d\n", i, names[o.kind], ms * 1e3, o.flops * 1e-9,
+                ms > 0 ? o.flops / (ms * 1e-3) * 1e-12 : 0.0, mt, N, BN, kb, T, S, H);
+      }
+      fclose(f);
+    }
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  if (se != cudaSuccess) return fail(c, (int)se, "profile run failed: %s", cudaGetErrorString(se));
+  return r;
+}
 extern "C" double sdxl_unet_alpha(const sdxl_unet* u, int i) {
   if (!u || i < 0 || i >= (int)u->alphas.size()) return NAN;
   return u->alphas[i];

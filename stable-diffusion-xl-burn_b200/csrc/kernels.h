@@ -9,6 +9,26 @@
 
 namespace sdxl {
 
+// Launch helper: cudaLaunchKernelEx with optional programmatic dependent launch (PDL). Kernels launched
+// with pdl=true MUST execute griddep_wait() (common.cuh) before touching global memory written by the
+// preceding kernel. SDXL_B200_NO_PDL=1 disables the attribute globally.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline int launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                         Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+  return (int)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Implicit GEMM on tcgen05 (igemm.cu): out[pixel, n] = epilogue( sum_seg sum_c A_seg[pixel+tap, c] *
 // Wt[n, k(seg,c)] ). Linear layers are the 1-segment / 1x1 case of the same kernel.
@@ -27,7 +47,7 @@ struct alignas(64) IgemmParams {
   int nseg;
   int Wt, Ht, Bt;             // A box in pixels, Wt*Ht*Bt == 128
   int W, H, Bn;               // output extents
-  int tilesW, tilesH, tilesB;
+  int tilesW, tilesH, tilesB, tilesN;
   int N;                      // valid output columns (GEGLU: columns of the fused [value|gate] GEMM)
   int BN;                     // N tile (multiple of 16, <= 256)
   int nstages;

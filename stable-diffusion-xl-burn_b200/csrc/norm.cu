@@ -17,6 +17,8 @@ size_t gn_scratch_floats(int B, int n_group) { return (size_t)B * kGnMaxChunk * 
 __global__ void gn_stats_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2, int HW,
                                 int n_group, int R, float* __restrict__ partial) {
   extern __shared__ float sm[];  // [R][C][2]
+  griddep_wait();
+  griddep_launch_dependents();
   const int C = C1 + C2;
   const int V = C >> 2;
   const int v = threadIdx.x % V, rr = threadIdx.x / V;
@@ -59,6 +61,8 @@ __global__ void gn_apply_kernel(const float* __restrict__ x1, int C1, const floa
                                 float eps, int silu, const float* __restrict__ partial, int nchunk,
                                 __half* __restrict__ y, __half* __restrict__ raw) {
   extern __shared__ float sm[];  // scale[C], shift[C], mean[G], rstd[G]
+  griddep_wait();
+  griddep_launch_dependents();
   const int C = C1 + C2;
   float* sc = sm;
   float* sh = sm + C;
@@ -145,17 +149,16 @@ int gn_launch(cudaStream_t st, GnParams& p) {
     cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     attr = true;
   }
-  gn_stats_kernel<<<dim3(nchunk, p.B), V * R, smem1, st>>>(p.x1, p.C1, p.x2, p.C2, p.HW, p.n_group, R, p.partial);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return (int)e;
+  int e = launch_kernel(gn_stats_kernel, dim3(nchunk, p.B), dim3(V * R), smem1, st, true, p.x1, p.C1, p.x2, p.C2, p.HW,
+                        p.n_group, R, p.partial);
+  if (e) return e;
   const size_t smem2 = (size_t)(2 * C + 2 * p.n_group) * sizeof(float);
   int ctas = cdiv((long)p.HW * (C / 8), 256 * 4);
   const int cap = (148 * 8) / (p.B > 0 ? p.B : 1);
   if (ctas > cap) ctas = cap;
   if (ctas < 1) ctas = 1;
-  gn_apply_kernel<<<dim3(ctas, p.B), 256, smem2, st>>>(p.x1, p.C1, p.x2, p.C2, p.HW, p.n_group, p.gamma, p.beta,
-                                                       p.eps, p.silu, p.partial, nchunk, p.y, p.raw);
-  return (int)cudaGetLastError();
+  return launch_kernel(gn_apply_kernel, dim3(ctas, p.B), dim3(256), smem2, st, true, p.x1, p.C1, p.x2, p.C2, p.HW,
+                       p.n_group, p.gamma, p.beta, p.eps, p.silu, (const float*)p.partial, nchunk, p.y, p.raw);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -166,6 +169,8 @@ template <int NV>
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, float eps, int rows, int C,
                                  __half* __restrict__ y) {
+  griddep_wait();
+  griddep_launch_dependents();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -215,13 +220,12 @@ int layernorm_launch(cudaStream_t st, const float* x, const float* gamma, const 
   const int nv = cdiv(C, 128);
   const int warps = 8;
   dim3 grid(cdiv(rows, warps));
-  if (nv <= 1) layernorm_kernel<1><<<grid, warps * 32, 0, st>>>(x, gamma, beta, eps, rows, C, y);
-  else if (nv <= 2) layernorm_kernel<2><<<grid, warps * 32, 0, st>>>(x, gamma, beta, eps, rows, C, y);
-  else if (nv <= 5) layernorm_kernel<5><<<grid, warps * 32, 0, st>>>(x, gamma, beta, eps, rows, C, y);
-  else if (nv <= 10) layernorm_kernel<10><<<grid, warps * 32, 0, st>>>(x, gamma, beta, eps, rows, C, y);
-  else if (nv <= 16) layernorm_kernel<16><<<grid, warps * 32, 0, st>>>(x, gamma, beta, eps, rows, C, y);
-  else return 3004;
-  return (int)cudaGetLastError();
+  if (nv <= 1) return launch_kernel(layernorm_kernel<1>, grid, dim3(warps * 32), (size_t)0, st, true, x, gamma, beta, eps, rows, C, y);
+  else if (nv <= 2) return launch_kernel(layernorm_kernel<2>, grid, dim3(warps * 32), (size_t)0, st, true, x, gamma, beta, eps, rows, C, y);
+  else if (nv <= 5) return launch_kernel(layernorm_kernel<5>, grid, dim3(warps * 32), (size_t)0, st, true, x, gamma, beta, eps, rows, C, y);
+  else if (nv <= 10) return launch_kernel(layernorm_kernel<10>, grid, dim3(warps * 32), (size_t)0, st, true, x, gamma, beta, eps, rows, C, y);
+  else if (nv <= 16) return launch_kernel(layernorm_kernel<16>, grid, dim3(warps * 32), (size_t)0, st, true, x, gamma, beta, eps, rows, C, y);
+  return 3004;
 }
 
 }  // namespace sdxl

@@ -310,6 +310,9 @@ class Diffuser:
         self.ctx.check(self.ctx.lib.sdxl_unet_profile_plan(self.h, ms, fl, ln), "sdxl_unet_profile_plan")
         return {n: {"ms": ms[i], "flops": fl[i], "launches": ln[i]} for i, n in enumerate(self.KIND_NAMES) if ln[i]}
 
+    def profile_dump(self, path: str) -> None:
+        self.ctx.check(self.ctx.lib.sdxl_unet_profile_dump(self.h, path.encode()), "sdxl_unet_profile_dump")
+
     def alpha(self, i: int) -> float:
         return float(self.ctx.lib.sdxl_unet_alpha(self.h, i))
 
