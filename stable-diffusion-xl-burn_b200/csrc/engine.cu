@@ -677,12 +677,6 @@ struct PlanBuilder {
     Op op{};
     op.kind = OP_IGEMM;
     IgemmParams& p = op.ig;
-    igemm_pick_box(outW, outH, &p.Wt, &p.Ht, &p.Bt);
-    p.W = outW; p.H = outH; p.Bn = outB;
-    const int m_tiles = ((outW + p.Wt - 1) / p.Wt) * ((outH + p.Ht - 1) / p.Ht) * ((outB + p.Bt - 1) / p.Bt);
-    p.N = N;
-    p.mode = mode;
-    p.BN = (mode == IGEMM_GEGLU) ? geglu_bn : igemm_pick_bn(m_tiles, N, c->num_sms, false);
     p.nseg = (int)segs.size();
     if (p.nseg > IGEMM_MAX_SEG) { err = fail(c, 5002, "too many igemm segments"); return; }
     for (int i = 0; i < p.nseg; ++i) p.seg[i] = segs[i];
@@ -690,11 +684,10 @@ struct PlanBuilder {
     p.bias = bias; p.bias_bstride = bias_bstride;
     p.res = res; p.ldr = ldr;
     if (!A->measure) {
-      int r = make_tmap_act(&p.tmA0, a0.p, a0.Bn, a0.H, a0.W, a0.C, a0.C, p.Wt, p.Ht, p.Bt);
-      if (!r && a1) r = make_tmap_act(&p.tmA1, a1->p, a1->Bn, a1->H, a1->W, a1->C, a1->C, p.Wt, p.Ht, p.Bt);
-      if (!r && !a1) p.tmA1 = p.tmA0;
-      if (!r) r = make_tmap_wgt(&p.tmB, W, N, Ktot, p.BN);
-      if (r) { err = fail(c, r, "tensor map creation failed (igemm N=%d K=%d)", N, Ktot); return; }
+      IgemmOperands o{a0.p, a0.Bn, a0.H, a0.W, a0.C, a0.C, a1 ? a1->p : nullptr, a1 ? a1->Bn : 0, a1 ? a1->H : 0,
+                      a1 ? a1->W : 0, a1 ? a1->C : 0, a1 ? a1->C : 0, W, N, Ktot};
+      int r = igemm_configure(p, o, outW, outH, outB, mode, geglu_bn);
+      if (r) { err = fail(c, r, "igemm configuration failed (N=%d K=%d)", N, Ktot); return; }
     }
     P->ops.push_back(op);
   }
@@ -1113,17 +1106,12 @@ static int set_conditioning_dev(sdxl_unet* u, int B, int n_ctx, const __half* co
     for (size_t i = 0; i < tbs.size(); ++i) {
       const Lin& L = tbs[i]->kv2;
       IgemmParams p{};
-      igemm_pick_box(M, 1, &p.Wt, &p.Ht, &p.Bt);
-      p.W = M; p.H = 1; p.Bn = 1;
-      const int m_tiles = (M + p.Wt - 1) / p.Wt;
-      p.N = L.N; p.mode = IGEMM_LINEAR;
-      p.BN = igemm_pick_bn(m_tiles, L.N, c->num_sms, false);
       p.nseg = 1;
       p.seg[0] = {0, 0, 0, 0, L.Kpad / 64};
       p.out = u->kv[i]; p.out_f32 = 0; p.ldo = L.N;
-      int r = make_tmap_act(&p.tmA0, u->ctx16, 1, 1, M, g.context_dim, u->ctx_pitch, p.Wt, p.Ht, p.Bt);
-      if (!r) { p.tmA1 = p.tmA0; r = make_tmap_wgt(&p.tmB, L.w, L.N, L.Kpad, p.BN); }
-      if (r) return fail(c, r, "tensor map creation failed (kv projection)");
+      IgemmOperands o{u->ctx16, 1, 1, M, g.context_dim, u->ctx_pitch, nullptr, 0, 0, 0, 0, 0, L.w, L.N, L.Kpad};
+      int r = igemm_configure(p, o, M, 1, 1, IGEMM_LINEAR, 0);
+      if (r) return fail(c, r, "igemm configuration failed (kv projection)");
       KL(c, igemm_launch(c->stream, p));
     }
   }
@@ -1214,7 +1202,7 @@ extern "C" int sdxl_unet_profile_dump(sdxl_unet* u, const char* path) {
     FILE* f = fopen(path, "w");
     if (!f) r = fail(c, -3, "cannot open %s", path);
     else {
-      fprintf(f, "op,kind,us,gflop,tflops,M_tiles,N,BN,Kblocks,T,S,heads\n");
+      fprintf(f, "op,kind,us,gflop,tflops,M_tiles,N,BN,Kblocks,T,S,heads,cluster\n");
       static const char* names[] = {"igemm", "attention", "group_norm", "layer_norm", "gemv", "temb", "conv_in", "upsample", "phase_split", "cast16"};
       for (size_t i = 0; i < n; ++i) {
         float ms = 0;
@@ -1225,8 +1213,9 @@ extern "C" int sdxl_unet_profile_dump(sdxl_unet* u, const char* path) {
           mt = o.ig.tilesW * o.ig.tilesH * o.ig.tilesB; N = o.ig.N; BN = o.ig.BN;
           for (int s2 = 0; s2 < o.ig.nseg; ++s2) kb += o.ig.seg[s2].nkb;
         } else if (o.kind == OP_ATTN) { T = o.at.T; S = o.at.S; H = o.at.n_head; }
-        fprintf(f, "%zu,%s,%.2f,%.3f,%.1f,%d,%d,%d,%d,%d,%d,%d\n", i, names[o.kind], ms * 1e3, o.flops * 1e-9,
-                ms > 0 ? o.flops / (ms * 1e-3) * 1e-12 : 0.0, mt, N, BN, kb, T, S, H);
+        fprintf(f, "%zu,%s,%.2f,%.3f,%.1f,%d,%d,%d,%d,%d,%d,%d,%dx%d\n", i, names[o.kind], ms * 1e3, o.flops * 1e-9,
+                ms > 0 ? o.flops / (ms * 1e-3) * 1e-12 : 0.0, mt, N, BN, kb, T, S, H, o.kind == OP_IGEMM ? o.ig.CM : 0,
+                o.kind == OP_IGEMM ? o.ig.CN : 0);
       }
       fclose(f);
     }
@@ -1491,11 +1480,6 @@ extern "C" int sdxl_op_linear(sdxl_ctx* c, const sdxl_half* x, const sdxl_half* 
   KL(c, transpose_linear_launch(c->stream, (const __half*)w, K, N, wt, Kpad, 0, gbn));
   if (bias) KL(c, bias_to_f32_launch(c->stream, (const __half*)bias, N, b32, gbn, 0));
   IgemmParams p{};
-  igemm_pick_box(M, 1, &p.Wt, &p.Ht, &p.Bt);
-  p.W = M; p.H = 1; p.Bn = 1;
-  p.N = N;
-  p.mode = geglu ? IGEMM_GEGLU : IGEMM_LINEAR;
-  p.BN = geglu ? gbn : igemm_pick_bn((M + p.Wt - 1) / p.Wt, N, c->num_sms, false);
   p.nseg = 1;
   p.seg[0] = {0, 0, 0, 0, Kpad / 64};
   p.out = out;
@@ -1503,9 +1487,9 @@ extern "C" int sdxl_op_linear(sdxl_ctx* c, const sdxl_half* x, const sdxl_half* 
   p.ldo = geglu ? N / 2 : N;
   p.bias = b32; p.bias_bstride = 0;
   p.res = geglu ? nullptr : residual; p.ldr = N;
-  int r = make_tmap_act(&p.tmA0, (const __half*)x, 1, 1, M, K, K, p.Wt, p.Ht, p.Bt);
-  if (!r) { p.tmA1 = p.tmA0; r = make_tmap_wgt(&p.tmB, wt, N, Kpad, p.BN); }
-  if (r) return fail(c, r, "tensor map creation failed");
+  IgemmOperands o{(const __half*)x, 1, 1, M, K, K, nullptr, 0, 0, 0, 0, 0, wt, N, Kpad};
+  int r = igemm_configure(p, o, M, 1, 1, geglu ? IGEMM_GEGLU : IGEMM_LINEAR, gbn);
+  if (r) return fail(c, r, "igemm configuration failed");
   KL(c, igemm_launch(c->stream, p));
   return 0;
 }
@@ -1546,16 +1530,11 @@ extern "C" int sdxl_op_conv2d(sdxl_ctx* c, const float* x, const sdxl_half* w, c
     for (int kh = 0; kh < ksize; ++kh)
       for (int kw = 0; kw < ksize; ++kw) p.seg[p.nseg++] = {0, (int16_t)(kw - pad), (int16_t)(kh - pad), 0, Ipad / 64};
   }
-  igemm_pick_box(Wo, Ho, &p.Wt, &p.Ht, &p.Bt);
-  p.W = Wo; p.H = Ho; p.Bn = B;
-  const int m_tiles = ((Wo + p.Wt - 1) / p.Wt) * ((Ho + p.Ht - 1) / p.Ht) * ((B + p.Bt - 1) / p.Bt);
-  p.N = Cout; p.mode = IGEMM_LINEAR;
-  p.BN = igemm_pick_bn(m_tiles, Cout, c->num_sms, false);
   p.out = out; p.out_f32 = 1; p.ldo = Cout;
   p.bias = b32; p.bias_bstride = 0; p.res = nullptr; p.ldr = 0;
-  int r = make_tmap_act(&p.tmA0, a.p, a.Bn, a.H, a.W, a.C, a.C, p.Wt, p.Ht, p.Bt);
-  if (!r) { p.tmA1 = p.tmA0; r = make_tmap_wgt(&p.tmB, wt, Cout, Ktot, p.BN); }
-  if (r) return fail(c, r, "tensor map creation failed");
+  IgemmOperands o{a.p, a.Bn, a.H, a.W, a.C, a.C, nullptr, 0, 0, 0, 0, 0, wt, Cout, Ktot};
+  int r = igemm_configure(p, o, Wo, Ho, B, IGEMM_LINEAR, 0);
+  if (r) return fail(c, r, "igemm configuration failed");
   KL(c, igemm_launch(c->stream, p));
   return 0;
 }

@@ -28,6 +28,32 @@ inline int launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t
   cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
   return (int)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+template <typename... KArgs, typename... Args>
+inline int launch_kernel_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                                 int cluster_size, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster_size > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_size;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl && pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return (int)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // ------------------------------------------------------------------------------------------------
 // Implicit GEMM on tcgen05 (igemm.cu): out[pixel, n] = epilogue( sum_seg sum_c A_seg[pixel+tap, c] *
@@ -48,6 +74,8 @@ struct alignas(64) IgemmParams {
   int Wt, Ht, Bt;             // A box in pixels, Wt*Ht*Bt == 128
   int W, H, Bn;               // output extents
   int tilesW, tilesH, tilesB, tilesN;
+  int CM, CN;                 // cluster shape (M x N CTAs sharing operand tiles via TMA multicast)
+  int a_split_dim, a_split_ext;  // how the A tile is sliced across the CN peers (0=W,1=H,2=B; extent per slice)
   int N;                      // valid output columns (GEGLU: columns of the fused [value|gate] GEMM)
   int BN;                     // N tile (multiple of 16, <= 256)
   int nstages;
@@ -67,7 +95,15 @@ int make_tmap_act(CUtensorMap* tm, const __half* base, int Bn, int H, int W, int
 int make_tmap_wgt(CUtensorMap* tm, const __half* base, int N, int K, int BN);
 // Picks Wt/Ht/Bt (product 128) for an output image of W x H.
 void igemm_pick_box(int W, int H, int* Wt, int* Ht, int* Bt);
-// Fills tiles*/nstages from the other fields and launches.
+// Operand views for igemm_configure: NHWC f16 activations (channel pitch in elements) and K-major weights.
+struct IgemmOperands {
+  const __half* a0; int a0Bn, a0H, a0W, a0C, a0pitch;
+  const __half* a1; int a1Bn, a1H, a1W, a1C, a1pitch;   // nullable second source (segments with map == 1)
+  const __half* w; int N, Ktot;
+};
+// Chooses the pixel box, N tile, cluster shape and pipeline depth, and builds the TMA descriptors. The caller
+// fills seg[]/nseg and the epilogue fields (out, out_f32, ldo, bias, bias_bstride, res, ldr).
+int igemm_configure(IgemmParams& p, const IgemmOperands& o, int outW, int outH, int outB, int mode, int geglu_bn);
 int igemm_launch(cudaStream_t st, IgemmParams& p);
 // Chooses an N tile for (M pixels, N columns) minimising wave-quantisation loss on `num_sms` SMs.
 int igemm_pick_bn(int m_tiles, int N, int num_sms, bool geglu);
