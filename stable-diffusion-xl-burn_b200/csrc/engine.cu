@@ -1214,8 +1214,8 @@ extern "C" int sdxl_unet_profile_dump(sdxl_unet* u, const char* path) {
           for (int s2 = 0; s2 < o.ig.nseg; ++s2) kb += o.ig.seg[s2].nkb;
         } else if (o.kind == OP_ATTN) { T = o.at.T; S = o.at.S; H = o.at.n_head; }
         fprintf(f, "%zu,%s,%.2f,%.3f,%.1f,%d,%d,%d,%d,%d,%d,%d,%dx%d\n", i, names[o.kind], ms * 1e3, o.flops * 1e-9,
-                ms > 0 ? o.flops / (ms * 1e-3) * 1e-12 : 0.0, mt, N, BN, kb, T, S, H, o.kind == OP_IGEMM ? o.ig.CM : 0,
-                o.kind == OP_IGEMM ? o.ig.CN : 0);
+                ms > 0 ? o.flops / (ms * 1e-3) * 1e-12 : 0.0, mt, N, BN, kb, T, S, H,
+                o.kind == OP_IGEMM ? (o.ig.pair ? 9 : o.ig.CM) : 0, o.kind == OP_IGEMM ? o.ig.CN : 0);
       }
       fclose(f);
     }

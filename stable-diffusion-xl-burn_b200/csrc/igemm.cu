@@ -62,6 +62,102 @@ __device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
                : "memory");
 }
 
+// Epilogue of one 128 x BN accumulator tile for the calling thread's row (TMEM lane): column chunks
+// [c_begin, c_end) of 16. LINEAR: out = acc + bias[b] (+ f32 residual) as f32 or f16. GEGLU: out = value*gelu(gate).
+__device__ __forceinline__ void epilogue_tile(const IgemmParams& p, uint32_t trow, int nt, int n0, bool row_ok, size_t pix,
+                                              int bb, int c_begin, int c_end) {
+  const int BN = p.BN;
+  if (p.mode == IGEMM_LINEAR) {
+    const float* bias = p.bias ? p.bias + (size_t)bb * p.bias_bstride : nullptr;
+    const float* res = p.res ? p.res + pix * p.ldr : nullptr;
+    for (int ch = c_begin; ch < c_end; ++ch) {
+      const int c = ch << 4;
+      uint32_t v[16];
+      tmem_ld16(trow + c, v);
+      tmem_ld_wait();
+      const int n = n0 + c;
+      if (row_ok && n < p.N) {
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+        if (n + 16 <= p.N) {
+          if (bias) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n + i));
+              f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+            }
+          }
+          if (res) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 r4 = *reinterpret_cast<const float4*>(res + n + i);
+              f[i] += r4.x; f[i + 1] += r4.y; f[i + 2] += r4.z; f[i + 3] += r4.w;
+            }
+          }
+          if (p.out_f32) {
+            float* o = reinterpret_cast<float*>(p.out) + pix * p.ldo + n;
+#pragma unroll
+            for (int i = 0; i < 16; i += 4)
+              *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+          } else {
+            __half* o = reinterpret_cast<__half*>(p.out) + pix * p.ldo + n;
+            uint32_t h[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              __half2 t = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+              h[i] = *reinterpret_cast<uint32_t*>(&t);
+            }
+            *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(o + 8) = make_uint4(h[4], h[5], h[6], h[7]);
+          }
+        } else {
+          // ragged N tail (e.g. the 320->4 output conv): scalar, guarded
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (n + i < p.N) {
+              float x = f[i];
+              if (bias) x += bias[n + i];
+              if (res) x += res[n + i];
+              if (p.out_f32) reinterpret_cast<float*>(p.out)[pix * p.ldo + n + i] = x;
+              else reinterpret_cast<__half*>(p.out)[pix * p.ldo + n + i] = __float2half_rn(x);
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // GEGLU (reference unet/mod.rs:942-956): tile columns [0,BN/2) = value, [BN/2,BN) = matching gate
+    const int hb = BN >> 1;
+    __half* o = reinterpret_cast<__half*>(p.out) + pix * p.ldo + (size_t)nt * hb;
+    for (int ch = c_begin; ch < c_end; ++ch) {
+      const int c = ch << 4;
+      uint32_t v[16], g[16];
+      tmem_ld16(trow + c, v);
+      tmem_ld16(trow + hb + c, g);
+      tmem_ld_wait();
+      if (row_ok && n0 + c < p.N) {
+        uint32_t h[8];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          float x0 = __uint_as_float(v[i]), x1 = __uint_as_float(v[i + 1]);
+          float g0 = __uint_as_float(g[i]), g1 = __uint_as_float(g[i + 1]);
+          if (p.bias) {
+            x0 += __ldg(p.bias + n0 + c + i);
+            x1 += __ldg(p.bias + n0 + c + i + 1);
+            g0 += __ldg(p.bias + n0 + hb + c + i);
+            g1 += __ldg(p.bias + n0 + hb + c + i + 1);
+          }
+          __half2 t = __floats2half2_rn(x0 * gelu_erf_f(g0), x1 * gelu_erf_f(g1));
+          h[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
+        }
+        *reinterpret_cast<uint4*>(o + c) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(o + c + 8) = make_uint4(h[4], h[5], h[6], h[7]);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages x (A 16KB | B BN*128)] [full][empty][tmem_full x2][tmem_empty x2][tmem ptr]
@@ -213,95 +309,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
 
-      if (p.mode == IGEMM_LINEAR) {
-        const float* bias = p.bias ? p.bias + (size_t)bb * p.bias_bstride : nullptr;
-        const float* res = p.res ? p.res + pix * p.ldr : nullptr;
-        for (int ch = c_begin; ch < c_end; ++ch) {
-          const int c = ch << 4;
-          uint32_t v[16];
-          tmem_ld16(trow + c, v);
-          tmem_ld_wait();
-          const int n = n0 + c;
-          if (row_ok && n < p.N) {
-            float f[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-            if (n + 16 <= p.N) {
-              if (bias) {
-#pragma unroll
-                for (int i = 0; i < 16; i += 4) {
-                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n + i));
-                  f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
-                }
-              }
-              if (res) {
-#pragma unroll
-                for (int i = 0; i < 16; i += 4) {
-                  const float4 r4 = *reinterpret_cast<const float4*>(res + n + i);
-                  f[i] += r4.x; f[i + 1] += r4.y; f[i + 2] += r4.z; f[i + 3] += r4.w;
-                }
-              }
-              if (p.out_f32) {
-                float* o = reinterpret_cast<float*>(p.out) + pix * p.ldo + n;
-#pragma unroll
-                for (int i = 0; i < 16; i += 4)
-                  *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-              } else {
-                __half* o = reinterpret_cast<__half*>(p.out) + pix * p.ldo + n;
-                uint32_t h[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  __half2 t = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
-                  h[i] = *reinterpret_cast<uint32_t*>(&t);
-                }
-                *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<uint4*>(o + 8) = make_uint4(h[4], h[5], h[6], h[7]);
-              }
-            } else {
-              // ragged N tail (e.g. the 320->4 output conv): scalar, guarded
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                if (n + i < p.N) {
-                  float x = f[i];
-                  if (bias) x += bias[n + i];
-                  if (res) x += res[n + i];
-                  if (p.out_f32) reinterpret_cast<float*>(p.out)[pix * p.ldo + n + i] = x;
-                  else reinterpret_cast<__half*>(p.out)[pix * p.ldo + n + i] = __float2half_rn(x);
-                }
-              }
-            }
-          }
-        }
-      } else {
-        // GEGLU (reference unet/mod.rs:942-956): tile columns [0,BN/2) = value, [BN/2,BN) = matching gate
-        const int hb = BN >> 1;
-        __half* o = reinterpret_cast<__half*>(p.out) + pix * p.ldo + (size_t)nt * hb;
-        for (int ch = c_begin; ch < c_end; ++ch) {
-          const int c = ch << 4;
-          uint32_t v[16], g[16];
-          tmem_ld16(trow + c, v);
-          tmem_ld16(trow + hb + c, g);
-          tmem_ld_wait();
-          if (row_ok && n0 + c < p.N) {
-            uint32_t h[8];
-#pragma unroll
-            for (int i = 0; i < 16; i += 2) {
-              float x0 = __uint_as_float(v[i]), x1 = __uint_as_float(v[i + 1]);
-              float g0 = __uint_as_float(g[i]), g1 = __uint_as_float(g[i + 1]);
-              if (p.bias) {
-                x0 += __ldg(p.bias + n0 + c + i);
-                x1 += __ldg(p.bias + n0 + c + i + 1);
-                g0 += __ldg(p.bias + n0 + hb + c + i);
-                g1 += __ldg(p.bias + n0 + hb + c + i + 1);
-              }
-              __half2 t = __floats2half2_rn(x0 * gelu_erf_f(g0), x1 * gelu_erf_f(g1));
-              h[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
-            }
-            *reinterpret_cast<uint4*>(o + c) = make_uint4(h[0], h[1], h[2], h[3]);
-            *reinterpret_cast<uint4*>(o + c + 8) = make_uint4(h[4], h[5], h[6], h[7]);
-          }
-        }
-      }
+      epilogue_tile(p, trow, nt, n0, row_ok, pix, bb, c_begin, c_end);
       // all TMEM reads of this buffer are complete (tcgen05.wait::ld above): hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -315,6 +323,218 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2-CTA variant (tcgen05 cta_group::2): a CTA pair (cluster of 2, same TPC) computes a 256 x BN tile with one
+// MMA stream issued by the leader CTA. Each CTA stages only ITS 128 A rows and HALF of the B tile (BN/2 weight
+// rows); the tensor core reads both halves across the pair, so the bytes delivered into each SM per FLOP drop by
+// 1/3 versus the 1-CTA kernel at BN = 256 (L2->SM delivery is what bounds these GEMMs). Accumulators: each CTA's
+// TMEM holds its own 128 rows x BN columns, double-buffered; epilogues run independently in both CTAs.
+// Barriers: full[s] lives in the leader and counts the TMA bytes of BOTH CTAs; empty[s] / tmem_full[b] are
+// signalled in both CTAs by the leader's multicast tcgen05.commit; tmem_empty[b] in the leader collects the
+// epilogue warps of both CTAs (the peer arrives remotely).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load into THIS CTA's smem whose completion bytes are credited to an mbarrier in the pair's leader CTA
+__device__ __forceinline__ void tma_load_4d_pair(void* dst, const void* tmap, uint32_t leader_bar, int c0, int c1, int c2,
+                                                 int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const void* tmap, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+          "r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {  // one warp in EACH CTA
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {  // arrive on `bar` in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1) igemm_pair_kernel(const __grid_constant__ IgemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int BN = p.BN;
+  const int nst = p.nstages;
+  const int b_rows = BN >> 1;                                  // this CTA's half of the B tile
+  const uint32_t stage_bytes = kABytes + b_rows * 128;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)nst * stage_bytes);
+  uint64_t* empty_bar = full_bar + nst;
+  uint64_t* tmem_full = empty_bar + nst;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;    // [2]  (used in the leader)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();  // 0 = leader
+  const int m_tiles = p.tilesW * p.tilesH * p.tilesB;
+  const int pm_tiles = m_tiles >> 1;
+  const int num_ptiles = pm_tiles * p.tilesN;
+  const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  int total_kb = 0;
+  for (int s = 0; s < p.nseg; ++s) total_kb += p.seg[s].nkb;
+
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)(2 * BN)) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA0);
+    tma_prefetch_desc(&p.tmA1);
+    tma_prefetch_desc(&p.tmB);
+    for (int i = 0; i < nst; ++i) {
+      mbar_init(&full_bar[i], 1);   // leader's producer arrives once with the byte count of both CTAs
+      mbar_init(&empty_bar[i], 1);  // leader's multicast commit
+    }
+    mbar_init(&tmem_full[0], 1);
+    mbar_init(&tmem_full[1], 1);
+    mbar_init(&tmem_empty[0], 2 * kEpiWarps);
+    mbar_init(&tmem_empty[1], 2 * kEpiWarps);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers exist before any cross-CTA signal
+  if (warp == 1) tmem_alloc_pair(tmem_ptr, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  griddep_wait();
+  griddep_launch_dependents();
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int pt = pair_id; pt < num_ptiles; pt += num_pairs) {
+        const int mt = (pt % pm_tiles) * 2 + rank, nt = pt / pm_tiles;
+        const int tw = mt % p.tilesW;
+        const int th = (mt / p.tilesW) % p.tilesH;
+        const int tb = mt / (p.tilesW * p.tilesH);
+        const int w0 = tw * p.Wt, h0 = th * p.Ht, b0 = tb * p.Bt;
+        const int n0 = nt * BN + rank * b_rows;
+        int kb = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const IgemmSeg sg = p.seg[s];
+          const void* mapA = sg.map ? (const void*)&p.tmA1 : (const void*)&p.tmA0;
+          for (int j = 0; j < sg.nkb; ++j, ++it, ++kb) {
+            const int stage = it % nst;
+            const uint32_t par = (it / nst) & 1;
+            mbar_wait(&empty_bar[stage], par ^ 1);
+            uint8_t* a_dst = smem + (size_t)stage * stage_bytes;
+            uint8_t* b_dst = a_dst + kABytes;
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * stage_bytes);
+            const uint32_t lbar = mapa_rank(smem_u32(&full_bar[stage]), 0);
+            tma_load_4d_pair(a_dst, mapA, lbar, j * kBlockK, w0 + sg.dw, h0 + sg.dh, b0 + sg.db);
+            tma_load_2d_pair(b_dst, &p.tmB, lbar, kb * kBlockK, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: one thread of the leader CTA =====================
+    if (rank == 0 && lane == 0) {
+      // M = 256 across the pair, N = BN
+      const uint32_t idesc = (1u << 4) | (((uint32_t)BN >> 3) << 17) | ((256u >> 4) << 24);
+      int it = 0, lt = 0;
+      for (int pt = pair_id; pt < num_ptiles; pt += num_pairs, ++lt) {
+        const int buf = lt & 1;
+        mbar_wait(&tmem_empty[buf], ((lt >> 1) & 1) ^ 1);  // both CTAs' epilogues drained this buffer
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+        for (int kb = 0; kb < total_kb; ++kb, ++it) {
+          const int stage = it % nst;
+          const uint32_t par = (it / nst) & 1;
+          mbar_wait(&full_bar[stage], par);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            tc_mma_f16_pair(d_tmem, make_sw128_desc(a_addr + k * 32), make_sw128_desc(b_addr + k * 32), idesc,
+                            (kb > 0 || k > 0) ? 1u : 0u);
+          tc_commit_pair(&empty_bar[stage]);  // frees the slot in both CTAs
+        }
+        tc_commit_pair(&tmem_full[buf]);      // accumulators (both halves) complete
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..9), both CTAs =====================
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    const int wt = r % p.Wt;
+    const int ht = (r / p.Wt) % p.Ht;
+    const int bt = r / (p.Wt * p.Ht);
+    const int nchunks = (p.mode == IGEMM_LINEAR ? BN : (BN >> 1)) >> 4;
+    const int c_begin = half == 0 ? 0 : ((nchunks + 1) >> 1);
+    const int c_end = half == 0 ? ((nchunks + 1) >> 1) : nchunks;
+    int lt = 0;
+    for (int pt = pair_id; pt < num_ptiles; pt += num_pairs, ++lt) {
+      const int mt = (pt % pm_tiles) * 2 + rank, nt = pt / pm_tiles;
+      const int tw = mt % p.tilesW;
+      const int th = (mt / p.tilesW) % p.tilesH;
+      const int tb = mt / (p.tilesW * p.tilesH);
+      const int bb = tb * p.Bt + bt, hh = th * p.Ht + ht, ww = tw * p.Wt + wt;
+      const int n0 = nt * BN;
+      const bool row_ok = (bb < p.Bn) && (hh < p.H) && (ww < p.W);
+      const size_t pix = ((size_t)bb * p.H + hh) * p.W + ww;
+      const int buf = lt & 1;
+      mbar_wait(&tmem_full[buf], (lt >> 1) & 1);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
+      epilogue_tile(p, trow, nt, n0, row_ok, pix, bb, c_begin, c_end);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(&tmem_empty[buf]);
+        else mbar_arrive_remote(mapa_rank(smem_u32(&tmem_empty[buf]), 0));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // peer finished reading its TMEM / signalling our barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, tmem_cols);
   }
 }
 
@@ -429,8 +649,8 @@ static int device_sms() {
   return num_sms;
 }
 
-static size_t igemm_smem_bytes(int nst, int BN) {
-  return (size_t)nst * (kABytes + BN * 128) + 1024 /*align slack*/ + (2 * nst + 4) * 8 + 16;
+static size_t igemm_smem_bytes(int nst, int b_rows) {
+  return (size_t)nst * (kABytes + b_rows * 128) + 1024 /*align slack*/ + (2 * nst + 4) * 8 + 16;
 }
 
 int igemm_configure(IgemmParams& p, const IgemmOperands& o, int outW, int outH, int outB, int mode, int geglu_bn) {
@@ -455,6 +675,11 @@ int igemm_configure(IgemmParams& p, const IgemmOperands& o, int outW, int outH, 
       CN = (p.tilesN % en == 0) ? en : 1;
     }
   }
+  // 2-CTA MMA (pair along M) is preferred whenever the M tile count is even: it is the only variant that
+  // lowers the bytes delivered per SM. SDXL_B200_PAIR=0 falls back to the 1-CTA (+multicast) kernel.
+  static const bool pair_on = !(getenv("SDXL_B200_PAIR") && getenv("SDXL_B200_PAIR")[0] == '0');
+  p.pair = (pair_on && m_tiles % 2 == 0 && (long)m_tiles * p.tilesN >= 4 && p.BN % 32 == 0) ? 1 : 0;
+  if (p.pair) { CM = 2; CN = 1; }
   p.CM = CM; p.CN = CN;
   // A slice (128/CN rows): split the slowest tile dimension that is >= CN
   int sWt = p.Wt, sHt = p.Ht, sBt = p.Bt;
@@ -469,7 +694,7 @@ int igemm_configure(IgemmParams& p, const IgemmOperands& o, int outW, int outH, 
   if (!r && !o.a1) p.tmA1 = p.tmA0;
   if (!r) r = make_tmap_wgt(&p.tmB, o.w, o.N, o.Ktot, p.BN / CM);
   if (r) return r;
-  const int stage_bytes = kABytes + p.BN * 128;
+  const int stage_bytes = kABytes + (p.pair ? p.BN * 64 : p.BN * 128);
   int nst = (224 * 1024) / stage_bytes;
   if (nst > 8) nst = 8;
   if (nst < 2) nst = 2;
@@ -478,10 +703,11 @@ int igemm_configure(IgemmParams& p, const IgemmOperands& o, int outW, int outH, 
 }
 
 int igemm_launch(cudaStream_t st, IgemmParams& p) {
-  const size_t smem = igemm_smem_bytes(p.nstages, p.BN);
+  const size_t smem = igemm_smem_bytes(p.nstages, p.pair ? p.BN / 2 : p.BN);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(igemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
@@ -508,6 +734,7 @@ int igemm_launch(cudaStream_t st, IgemmParams& p) {
     max_clusters[cs] = n;
   }
   const int nclusters = num_super < max_clusters[cs] ? num_super : max_clusters[cs];
+  if (p.pair) return launch_kernel_cluster(igemm_pair_kernel, dim3(nclusters * 2), dim3(kThreads), smem, st, true, 2, p);
   return launch_kernel_cluster(igemm_kernel, dim3(nclusters * cs), dim3(kThreads), smem, st, true, cs, p);
 }
 

@@ -74,6 +74,7 @@ struct alignas(64) IgemmParams {
   int Wt, Ht, Bt;             // A box in pixels, Wt*Ht*Bt == 128
   int W, H, Bn;               // output extents
   int tilesW, tilesH, tilesB, tilesN;
+  int pair;                   // 1: 2-CTA MMA kernel (cta_group::2), CM = 2, CN = 1
   int CM, CN;                 // cluster shape (M x N CTAs sharing operand tiles via TMA multicast)
   int a_split_dim, a_split_ext;  // how the A tile is sliced across the CN peers (0=W,1=H,2=B; extent per slice)
   int N;                      // valid output columns (GEGLU: columns of the fused [value|gate] GEMM)
