@@ -153,6 +153,10 @@ SDXL_API int sdxl_unet_profile_plan(sdxl_unet* unet, double* ms_by_kind_host, do
                                     int* launches_by_kind_host);
 /* Same measurement, one CSV row per launch (analysis aid; written to `path_host`). */
 SDXL_API int sdxl_unet_profile_dump(sdxl_unet* unet, const char* path_host);
+/* Diagnostics: in-kernel timeline (ns, %globaltimer) of CTA 0 of one implicit-GEMM launch on a synthetic
+ * [M,K]x[K,N] problem; stamps_host[9]: see csrc/engine.cu. */
+SDXL_API int sdxl_dbg_igemm_timeline(sdxl_ctx* ctx, int M, int K, int N, int geglu, int with_residual,
+                                     uint64_t* stamps_host);
 /* seeded N(0,1) exactly as the sampler generates it (device out). */
 SDXL_API int sdxl_randn(sdxl_ctx* ctx, float* out, size_t n, uint64_t seed, uint64_t subsequence);
 

@@ -1566,3 +1566,53 @@ extern "C" int sdxl_op_timestep_embedding(sdxl_ctx* c, const int32_t* t_host, in
   CU(c, cudaStreamSynchronize(c->stream));  // t_host is pageable caller memory
   return 0;
 }
+
+// Diagnostics: in-kernel timeline (%globaltimer, ns) of CTA 0 of one igemm launch on a synthetic [M,K]x[K,N] problem.
+// stamps_host[0..6] = prologue done, dependencies resolved, first operands landed, first accumulator complete,
+// first epilogue done, producer done, all roles done; stamps_host[7] = CUDA-event duration of the launch in ns.
+extern "C" int sdxl_dbg_igemm_timeline(sdxl_ctx* c, int M, int K, int N, int geglu, int with_residual, uint64_t* stamps_host) {
+  if (!c || !stamps_host) return -1;
+  TmpBufs T(c->stream);
+  const int Kpad = (K + 63) / 64 * 64;
+  int gbn = geglu ? geglu_bn_for(N / 2) : 0;
+  __half* x = (__half*)T.get((size_t)M * K * 2);
+  __half* w = (__half*)T.get((size_t)N * Kpad * 2);
+  float* bias = (float*)T.get((size_t)N * 4);
+  float* res = (float*)T.get((size_t)M * N * 4);
+  void* out = T.get((size_t)M * N * 4);
+  unsigned long long* dbg = (unsigned long long*)T.get(8 * 8);
+  if (!x || !w || !bias || !res || !out || !dbg) return fail(c, 5400, "temporary allocation failed");
+  CU(c, cudaMemsetAsync(x, 0, (size_t)M * K * 2, c->stream));
+  CU(c, cudaMemsetAsync(w, 0, (size_t)N * Kpad * 2, c->stream));
+  CU(c, cudaMemsetAsync(bias, 0, (size_t)N * 4, c->stream));
+  CU(c, cudaMemsetAsync(res, 0, (size_t)M * N * 4, c->stream));
+  CU(c, cudaMemsetAsync(dbg, 0, 64, c->stream));
+  IgemmParams p{};
+  p.nseg = 1;
+  p.seg[0] = {0, 0, 0, 0, Kpad / 64};
+  p.out = out; p.out_f32 = geglu ? 0 : 1; p.ldo = geglu ? N / 2 : N;
+  p.bias = bias; p.bias_bstride = 0;
+  p.res = (geglu || !with_residual) ? nullptr : res; p.ldr = N;
+  IgemmOperands o{x, 1, 1, M, K, K, nullptr, 0, 0, 0, 0, 0, w, N, Kpad};
+  int r = igemm_configure(p, o, M, 1, 1, geglu ? IGEMM_GEGLU : IGEMM_LINEAR, gbn);
+  if (r) return fail(c, r, "igemm configuration failed");
+  cudaEvent_t e0, e1;
+  CU(c, cudaEventCreate(&e0));
+  CU(c, cudaEventCreate(&e1));
+  if (getenv("SDXL_B200_DBG_MODE")) p.dbg_mode = atoi(getenv("SDXL_B200_DBG_MODE"));
+  if (getenv("SDXL_B200_DBG_NST")) p.nstages = atoi(getenv("SDXL_B200_DBG_NST"));
+  for (int i = 0; i < 3; ++i) KL(c, igemm_launch(c->stream, p));
+  p.dbg = dbg;
+  CU(c, cudaEventRecord(e0, c->stream));
+  KL(c, igemm_launch(c->stream, p));
+  CU(c, cudaEventRecord(e1, c->stream));
+  CU(c, cudaMemcpyAsync(stamps_host, dbg, 56, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  stamps_host[7] = (uint64_t)(ms * 1e6);
+  stamps_host[8] = (uint64_t)p.BN | ((uint64_t)p.pair << 16) | ((uint64_t)p.CM << 20) | ((uint64_t)p.CN << 24) | ((uint64_t)p.nstages << 28);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return 0;
+}

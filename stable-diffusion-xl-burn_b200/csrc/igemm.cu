@@ -62,69 +62,87 @@ __device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
                : "memory");
 }
 
+// Residual prefetch for one 16-column chunk (4 x float4 per thread). Issued one chunk ahead of its use (and, for the
+// first chunk of a tile, before the accumulator is even complete) so the L2 latency hides under TMEM loads / MMAs.
+struct ResChunk { float4 v[4]; };
+__device__ __forceinline__ ResChunk prefetch_res(const IgemmParams& p, bool row_ok, size_t pix, int n) {
+  ResChunk r;
+  if (p.res != nullptr && row_ok && n + 16 <= p.N) {
+    const float4* src = reinterpret_cast<const float4*>(p.res + pix * p.ldr + n);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r.v[i] = src[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  return r;
+}
+
 // Epilogue of one 128 x BN accumulator tile for the calling thread's row (TMEM lane): column chunks
 // [c_begin, c_end) of 16. LINEAR: out = acc + bias[b] (+ f32 residual) as f32 or f16. GEGLU: out = value*gelu(gate).
+// `rfirst` is the already-prefetched residual of chunk c_begin (LINEAR only).
 __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, uint32_t trow, int nt, int n0, bool row_ok, size_t pix,
-                                              int bb, int c_begin, int c_end) {
+                                              int bb, int c_begin, int c_end, ResChunk rfirst) {
   const int BN = p.BN;
   if (p.mode == IGEMM_LINEAR) {
     const float* bias = p.bias ? p.bias + (size_t)bb * p.bias_bstride : nullptr;
-    const float* res = p.res ? p.res + pix * p.ldr : nullptr;
+    ResChunk rcur = rfirst;
     for (int ch = c_begin; ch < c_end; ++ch) {
       const int c = ch << 4;
       uint32_t v[16];
       tmem_ld16(trow + c, v);
-      tmem_ld_wait();
       const int n = n0 + c;
-      if (row_ok && n < p.N) {
+      // next chunk's residual and this chunk's bias are in flight while the TMEM load completes
+      ResChunk rnext = (ch + 1 < c_end) ? prefetch_res(p, row_ok, pix, n + 16) : rcur;
+      float4 b4[4];
+      const bool full = row_ok && (n + 16 <= p.N);
+      if (bias != nullptr && full) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) b4[i] = __ldg(reinterpret_cast<const float4*>(bias + n) + i);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) b4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      tmem_ld_wait();
+      if (full) {
         float f[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-        if (n + 16 <= p.N) {
-          if (bias) {
+        for (int i = 0; i < 4; ++i) {
+          f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b4[i].x + rcur.v[i].x;
+          f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4[i].y + rcur.v[i].y;
+          f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4[i].z + rcur.v[i].z;
+          f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4[i].w + rcur.v[i].w;
+        }
+        if (p.out_f32) {
+          float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.ldo + n);
 #pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n + i));
-              f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
-            }
-          }
-          if (res) {
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              const float4 r4 = *reinterpret_cast<const float4*>(res + n + i);
-              f[i] += r4.x; f[i + 1] += r4.y; f[i + 2] += r4.z; f[i + 3] += r4.w;
-            }
-          }
-          if (p.out_f32) {
-            float* o = reinterpret_cast<float*>(p.out) + pix * p.ldo + n;
-#pragma unroll
-            for (int i = 0; i < 16; i += 4)
-              *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-          } else {
-            __half* o = reinterpret_cast<__half*>(p.out) + pix * p.ldo + n;
-            uint32_t h[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              __half2 t = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
-              h[i] = *reinterpret_cast<uint32_t*>(&t);
-            }
-            *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
-            *reinterpret_cast<uint4*>(o + 8) = make_uint4(h[4], h[5], h[6], h[7]);
-          }
+          for (int i = 0; i < 4; ++i) o[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
         } else {
-          // ragged N tail (e.g. the 320->4 output conv): scalar, guarded
+          __half* o = reinterpret_cast<__half*>(p.out) + pix * p.ldo + n;
+          uint32_t h[8];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            if (n + i < p.N) {
-              float x = f[i];
-              if (bias) x += bias[n + i];
-              if (res) x += res[n + i];
-              if (p.out_f32) reinterpret_cast<float*>(p.out)[pix * p.ldo + n + i] = x;
-              else reinterpret_cast<__half*>(p.out)[pix * p.ldo + n + i] = __float2half_rn(x);
-            }
+          for (int i = 0; i < 8; ++i) {
+            __half2 t = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+            h[i] = *reinterpret_cast<uint32_t*>(&t);
+          }
+          *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(o + 8) = make_uint4(h[4], h[5], h[6], h[7]);
+        }
+      } else if (row_ok && n < p.N) {
+        // ragged N tail (e.g. the 320->4 output conv): scalar, guarded
+        const float* res = p.res ? p.res + pix * p.ldr : nullptr;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          if (n + i < p.N) {
+            float x = __uint_as_float(v[i]);
+            if (bias) x += bias[n + i];
+            if (res) x += res[n + i];
+            if (p.out_f32) reinterpret_cast<float*>(p.out)[pix * p.ldo + n + i] = x;
+            else reinterpret_cast<__half*>(p.out)[pix * p.ldo + n + i] = __float2half_rn(x);
           }
         }
       }
+      rcur = rnext;
     }
   } else {
     // GEGLU (reference unet/mod.rs:942-956): tile columns [0,BN/2) = value, [BN/2,BN) = matching gate
@@ -135,19 +153,26 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, uint32_t tro
       uint32_t v[16], g[16];
       tmem_ld16(trow + c, v);
       tmem_ld16(trow + hb + c, g);
+      float4 bv[4], bg[4];
+      if (p.bias != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          bv[i] = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c) + i);
+          bg[i] = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + hb + c) + i);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) bv[i] = bg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       tmem_ld_wait();
       if (row_ok && n0 + c < p.N) {
+        const float* fbv = reinterpret_cast<const float*>(bv);
+        const float* fbg = reinterpret_cast<const float*>(bg);
         uint32_t h[8];
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
-          float x0 = __uint_as_float(v[i]), x1 = __uint_as_float(v[i + 1]);
-          float g0 = __uint_as_float(g[i]), g1 = __uint_as_float(g[i + 1]);
-          if (p.bias) {
-            x0 += __ldg(p.bias + n0 + c + i);
-            x1 += __ldg(p.bias + n0 + c + i + 1);
-            g0 += __ldg(p.bias + n0 + hb + c + i);
-            g1 += __ldg(p.bias + n0 + hb + c + i + 1);
-          }
+          const float x0 = __uint_as_float(v[i]) + fbv[i], x1 = __uint_as_float(v[i + 1]) + fbv[i + 1];
+          const float g0 = __uint_as_float(g[i]) + fbg[i], g1 = __uint_as_float(g[i + 1]) + fbg[i + 1];
           __half2 t = __floats2half2_rn(x0 * gelu_erf_f(g0), x1 * gelu_erf_f(g1));
           h[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
         }
@@ -209,8 +234,11 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   const uint32_t tmem_base = *tmem_ptr;
 
   // PDL: everything above overlapped the previous kernel's tail; from here on we touch its outputs.
+  const bool dbg = p.dbg != nullptr && blockIdx.x == 0;
+  if (dbg && threadIdx.x == 0) p.dbg[0] = globaltimer_ns();   // prologue done (before griddep wait)
   griddep_wait();
   griddep_launch_dependents();
+  if (dbg && threadIdx.x == 0) p.dbg[1] = globaltimer_ns();   // dependencies resolved
 
   // multicast masks (bit = CTA rank in cluster): A goes to my cluster row (same cm_idx), B to my column
   uint16_t row_mask = 0, col_mask = 0;
@@ -220,68 +248,79 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      int it = 0;
-      for (int st = cluster_id; st < num_super; st += num_clusters) {
-        const int mt = (st % m_super) * CM + cm_idx, nt = (st / m_super) * CN + cn_idx;
-        const int tw = mt % p.tilesW;
-        const int th = (mt / p.tilesW) % p.tilesH;
-        const int tb = mt / (p.tilesW * p.tilesH);
-        // my slice of the A tile: offset cn_idx * a_split_ext along the split dimension
-        int w0 = tw * p.Wt, h0 = th * p.Ht, b0 = tb * p.Bt;
-        if (p.a_split_dim == 0) w0 += cn_idx * p.a_split_ext;
-        else if (p.a_split_dim == 1) h0 += cn_idx * p.a_split_ext;
-        else b0 += cn_idx * p.a_split_ext;
-        const int n0 = nt * BN + cm_idx * b_rows;
-        int kb = 0;
-        for (int s = 0; s < p.nseg; ++s) {
-          const IgemmSeg sg = p.seg[s];
-          const void* mapA = sg.map ? (const void*)&p.tmA1 : (const void*)&p.tmA0;
-          for (int j = 0; j < sg.nkb; ++j, ++it, ++kb) {
-            const int stage = it % nst;
-            const uint32_t par = (it / nst) & 1;
-            mbar_wait(&empty_bar[stage], par ^ 1);
+    // The whole warp walks the loop (warp-uniform control flow keeps addresses in uniform registers); lane 0 issues.
+    uint32_t stage = 0, phase = 0;
+    for (int st = cluster_id; st < num_super; st += num_clusters) {
+      const int mt = (st % m_super) * CM + cm_idx, nt = (st / m_super) * CN + cn_idx;
+      const int tw = mt % p.tilesW;
+      const int th = (mt / p.tilesW) % p.tilesH;
+      const int tb = mt / (p.tilesW * p.tilesH);
+      // my slice of the A tile: offset cn_idx * a_split_ext along the split dimension
+      int w0 = tw * p.Wt, h0 = th * p.Ht, b0 = tb * p.Bt;
+      if (p.a_split_dim == 0) w0 += cn_idx * p.a_split_ext;
+      else if (p.a_split_dim == 1) h0 += cn_idx * p.a_split_ext;
+      else b0 += cn_idx * p.a_split_ext;
+      const int n0 = nt * BN + cm_idx * b_rows;
+      int kcol = 0;
+      for (int s = 0; s < p.nseg; ++s) {
+        const IgemmSeg sg = p.seg[s];
+        const void* mapA = sg.map ? (const void*)&p.tmA1 : (const void*)&p.tmA0;
+        const int cw = w0 + sg.dw, chh = h0 + sg.dh, cb = b0 + sg.db;
+        for (int j = 0; j < sg.nkb; ++j, kcol += kBlockK) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (lane == 0) {
             uint8_t* a_dst = smem + (size_t)stage * stage_bytes + (size_t)cn_idx * a_rows * 128;
             uint8_t* b_dst = smem + (size_t)stage * stage_bytes + kABytes + (size_t)cm_idx * b_rows * 128;
-            mbar_expect_tx(&full_bar[stage], stage_bytes);
-            if (CN > 1) tma_load_4d_mc(a_dst, mapA, &full_bar[stage], j * kBlockK, w0 + sg.dw, h0 + sg.dh, b0 + sg.db, row_mask);
-            else tma_load_4d(a_dst, mapA, &full_bar[stage], j * kBlockK, w0 + sg.dw, h0 + sg.dh, b0 + sg.db);
-            if (CM > 1) tma_load_2d_mc(b_dst, &p.tmB, &full_bar[stage], kb * kBlockK, n0, col_mask);
-            else tma_load_2d(b_dst, &p.tmB, &full_bar[stage], kb * kBlockK, n0);
+            if (p.dbg_mode == 1) {
+              mbar_arrive(&full_bar[stage]);
+            } else {
+              mbar_expect_tx(&full_bar[stage], stage_bytes);
+              if (CN > 1) tma_load_4d_mc(a_dst, mapA, &full_bar[stage], j * kBlockK, cw, chh, cb, row_mask);
+              else tma_load_4d(a_dst, mapA, &full_bar[stage], j * kBlockK, cw, chh, cb);
+              if (CM > 1) tma_load_2d_mc(b_dst, &p.tmB, &full_bar[stage], kcol, n0, col_mask);
+              else tma_load_2d(b_dst, &p.tmB, &full_bar[stage], kcol, n0);
+            }
           }
+          __syncwarp();
+          if (++stage == (uint32_t)nst) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16((uint32_t)BN, false);
-      const uint16_t release_mask = row_mask | col_mask;
-      int it = 0, lt = 0;
-      for (int st = cluster_id; st < num_super; st += num_clusters, ++lt) {
-        const int buf = lt & 1;
-        mbar_wait(&tmem_empty[buf], ((lt >> 1) & 1) ^ 1);  // epilogue drained this accumulator buffer
+    // ===================== MMA issuer: warp-uniform loop, lane 0 issues =====================
+    const uint32_t idesc = make_idesc_f16((uint32_t)BN, false);
+    const uint16_t release_mask = row_mask | col_mask;
+    const uint32_t desc_hi = 64u /*SBO=1024B>>4*/ | (1u << 14) /*version*/ | (2u << 29) /*SWIZZLE_128B*/;
+    const uint32_t a_lo0 = ((smem_u32(smem) >> 4) & 0x3FFFu) | (1u << 16);
+    const uint32_t stage_inc = stage_bytes >> 4, b_off = kABytes >> 4;
+    uint32_t stage = 0, phase = 0;
+    int lt = 0;
+    for (int st = cluster_id; st < num_super; st += num_clusters, ++lt) {
+      const int buf = lt & 1;
+      mbar_wait(&tmem_empty[buf], ((lt >> 1) & 1) ^ 1);  // epilogue drained this accumulator buffer
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+      for (int kb = 0; kb < total_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        if (dbg && lt == 0 && kb == 0 && lane == 0) p.dbg[2] = globaltimer_ns();  // first operands landed
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
-        for (int kb = 0; kb < total_kb; ++kb, ++it) {
-          const int stage = it % nst;
-          const uint32_t par = (it / nst) & 1;
-          mbar_wait(&full_bar[stage], par);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint32_t b_addr = a_addr + kABytes;
+        if (lane == 0) {
+          const uint32_t a_lo = a_lo0 + stage * stage_inc, b_lo = a_lo + b_off;
+          if (p.dbg_mode != 2) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            const uint64_t ad = make_sw128_desc(a_addr + k * 32);
-            const uint64_t bd = make_sw128_desc(b_addr + k * 32);
-            tc_mma_f16(d_tmem, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < kBlockK / 16; ++k)
+              tc_mma_f16(d_tmem, ((uint64_t)desc_hi << 32) | (a_lo + 2 * k), ((uint64_t)desc_hi << 32) | (b_lo + 2 * k), idesc,
+                         (kb > 0 || k > 0) ? 1u : 0u);
           }
           // free the smem slot (here and in every CTA whose loads land in it) once these MMAs have read it
           if (cs > 1) tc_commit_mc(&empty_bar[stage], release_mask);
           else tc_commit(&empty_bar[stage]);
         }
-        tc_commit(&tmem_full[buf]);  // accumulator of this tile complete
+        __syncwarp();
+        if (++stage == (uint32_t)nst) { stage = 0; phase ^= 1; }
       }
+      if (lane == 0) tc_commit(&tmem_full[buf]);  // accumulator of this tile complete
+      __syncwarp();
     }
   } else {
     // ===================== epilogue warps (2..9) =====================
@@ -305,20 +344,25 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       const bool row_ok = (bb < p.Bn) && (hh < p.H) && (ww < p.W);
       const size_t pix = ((size_t)bb * p.H + hh) * p.W + ww;
       const int buf = lt & 1;
+      const ResChunk rfirst = prefetch_res(p, row_ok, pix, n0 + (c_begin << 4));
       mbar_wait(&tmem_full[buf], (lt >> 1) & 1);
+      if (dbg && lt == 0 && threadIdx.x == 64) p.dbg[3] = globaltimer_ns();  // first accumulator complete
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
 
-      epilogue_tile(p, trow, nt, n0, row_ok, pix, bb, c_begin, c_end);
+      epilogue_tile(p, trow, nt, n0, row_ok, pix, bb, c_begin, c_end, rfirst);
       // all TMEM reads of this buffer are complete (tcgen05.wait::ld above): hand it back to the MMA warp
+      if (dbg && lt == 0 && threadIdx.x == 64) p.dbg[4] = globaltimer_ns();  // first epilogue done
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
     }
   }
 
+  if (dbg && threadIdx.x == 0) p.dbg[5] = globaltimer_ns();  // producer done issuing
   tc_fence_before();
   __syncthreads();
+  if (dbg && threadIdx.x == 0) p.dbg[6] = globaltimer_ns();  // all roles done
   if (cs > 1) cluster_sync_all();  // no CTA leaves while a peer may still signal its barriers
   if (warp == 1) {
     tc_fence_after();
@@ -435,63 +479,80 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_pair_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
+  const bool dbg = p.dbg != nullptr && blockIdx.x == 0;
+  if (dbg && threadIdx.x == 0) p.dbg[0] = globaltimer_ns();   // prologue done (before griddep wait)
   griddep_wait();
   griddep_launch_dependents();
+  if (dbg && threadIdx.x == 0) p.dbg[1] = globaltimer_ns();   // dependencies resolved
 
   if (warp == 0) {
-    // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
-      int it = 0;
-      for (int pt = pair_id; pt < num_ptiles; pt += num_pairs) {
-        const int mt = (pt % pm_tiles) * 2 + rank, nt = pt / pm_tiles;
-        const int tw = mt % p.tilesW;
-        const int th = (mt / p.tilesW) % p.tilesH;
-        const int tb = mt / (p.tilesW * p.tilesH);
-        const int w0 = tw * p.Wt, h0 = th * p.Ht, b0 = tb * p.Bt;
-        const int n0 = nt * BN + rank * b_rows;
-        int kb = 0;
-        for (int s = 0; s < p.nseg; ++s) {
-          const IgemmSeg sg = p.seg[s];
-          const void* mapA = sg.map ? (const void*)&p.tmA1 : (const void*)&p.tmA0;
-          for (int j = 0; j < sg.nkb; ++j, ++it, ++kb) {
-            const int stage = it % nst;
-            const uint32_t par = (it / nst) & 1;
-            mbar_wait(&empty_bar[stage], par ^ 1);
+    // ===================== TMA producer (both CTAs): warp-uniform loop, lane 0 issues =====================
+    uint32_t stage = 0, phase = 0;
+    for (int pt = pair_id; pt < num_ptiles; pt += num_pairs) {
+      const int mt = (pt % pm_tiles) * 2 + rank, nt = pt / pm_tiles;
+      const int tw = mt % p.tilesW;
+      const int th = (mt / p.tilesW) % p.tilesH;
+      const int tb = mt / (p.tilesW * p.tilesH);
+      const int w0 = tw * p.Wt, h0 = th * p.Ht, b0 = tb * p.Bt;
+      const int n0 = nt * BN + rank * b_rows;
+      int kcol = 0;
+      for (int s = 0; s < p.nseg; ++s) {
+        const IgemmSeg sg = p.seg[s];
+        const void* mapA = sg.map ? (const void*)&p.tmA1 : (const void*)&p.tmA0;
+        const int cw = w0 + sg.dw, chh = h0 + sg.dh, cb = b0 + sg.db;
+        for (int j = 0; j < sg.nkb; ++j, kcol += kBlockK) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (lane == 0) {
             uint8_t* a_dst = smem + (size_t)stage * stage_bytes;
             uint8_t* b_dst = a_dst + kABytes;
-            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * stage_bytes);
-            const uint32_t lbar = mapa_rank(smem_u32(&full_bar[stage]), 0);
-            tma_load_4d_pair(a_dst, mapA, lbar, j * kBlockK, w0 + sg.dw, h0 + sg.dh, b0 + sg.db);
-            tma_load_2d_pair(b_dst, &p.tmB, lbar, kb * kBlockK, n0);
+            if (p.dbg_mode == 1) {
+              if (rank == 0) mbar_arrive(&full_bar[stage]);
+            } else {
+              if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * stage_bytes);
+              const uint32_t lbar = mapa_rank(smem_u32(&full_bar[stage]), 0);
+              tma_load_4d_pair(a_dst, mapA, lbar, j * kBlockK, cw, chh, cb);
+              tma_load_2d_pair(b_dst, &p.tmB, lbar, kcol, n0);
+            }
           }
+          __syncwarp();
+          if (++stage == (uint32_t)nst) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer: one thread of the leader CTA =====================
-    if (rank == 0 && lane == 0) {
+    // ===================== MMA issuer: leader CTA, warp-uniform loop, lane 0 issues =====================
+    if (rank == 0) {
       // M = 256 across the pair, N = BN
       const uint32_t idesc = (1u << 4) | (((uint32_t)BN >> 3) << 17) | ((256u >> 4) << 24);
-      int it = 0, lt = 0;
+      const uint32_t desc_hi = 64u | (1u << 14) | (2u << 29);
+      const uint32_t a_lo0 = ((smem_u32(smem) >> 4) & 0x3FFFu) | (1u << 16);
+      const uint32_t stage_inc = stage_bytes >> 4, b_off = kABytes >> 4;
+      uint32_t stage = 0, phase = 0;
+      int lt = 0;
       for (int pt = pair_id; pt < num_ptiles; pt += num_pairs, ++lt) {
         const int buf = lt & 1;
         mbar_wait(&tmem_empty[buf], ((lt >> 1) & 1) ^ 1);  // both CTAs' epilogues drained this buffer
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
-        for (int kb = 0; kb < total_kb; ++kb, ++it) {
-          const int stage = it % nst;
-          const uint32_t par = (it / nst) & 1;
-          mbar_wait(&full_bar[stage], par);
+        for (int kb = 0; kb < total_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          if (dbg && lt == 0 && kb == 0 && lane == 0) p.dbg[2] = globaltimer_ns();  // first operands landed
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint32_t b_addr = a_addr + kABytes;
+          if (lane == 0) {
+            const uint32_t a_lo = a_lo0 + stage * stage_inc, b_lo = a_lo + b_off;
+            if (p.dbg_mode != 2) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
-            tc_mma_f16_pair(d_tmem, make_sw128_desc(a_addr + k * 32), make_sw128_desc(b_addr + k * 32), idesc,
-                            (kb > 0 || k > 0) ? 1u : 0u);
-          tc_commit_pair(&empty_bar[stage]);  // frees the slot in both CTAs
+              for (int k = 0; k < kBlockK / 16; ++k)
+                tc_mma_f16_pair(d_tmem, ((uint64_t)desc_hi << 32) | (a_lo + 2 * k), ((uint64_t)desc_hi << 32) | (b_lo + 2 * k),
+                                idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            tc_commit_pair(&empty_bar[stage]);  // frees the slot in both CTAs
+          }
+          __syncwarp();
+          if (++stage == (uint32_t)nst) { stage = 0; phase ^= 1; }
         }
-        tc_commit_pair(&tmem_full[buf]);      // accumulators (both halves) complete
+        if (lane == 0) tc_commit_pair(&tmem_full[buf]);  // accumulators (both halves) complete
+        __syncwarp();
       }
     }
   } else {
@@ -516,10 +577,13 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_pair_kernel(const __grid_co
       const bool row_ok = (bb < p.Bn) && (hh < p.H) && (ww < p.W);
       const size_t pix = ((size_t)bb * p.H + hh) * p.W + ww;
       const int buf = lt & 1;
+      const ResChunk rfirst = prefetch_res(p, row_ok, pix, n0 + (c_begin << 4));
       mbar_wait(&tmem_full[buf], (lt >> 1) & 1);
+      if (dbg && lt == 0 && threadIdx.x == 64) p.dbg[3] = globaltimer_ns();  // first accumulator complete
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
-      epilogue_tile(p, trow, nt, n0, row_ok, pix, bb, c_begin, c_end);
+      epilogue_tile(p, trow, nt, n0, row_ok, pix, bb, c_begin, c_end, rfirst);
+      if (dbg && lt == 0 && threadIdx.x == 64) p.dbg[4] = globaltimer_ns();  // first epilogue done
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -529,8 +593,10 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_pair_kernel(const __grid_co
     }
   }
 
+  if (dbg && threadIdx.x == 0) p.dbg[5] = globaltimer_ns();  // producer done issuing
   tc_fence_before();
   __syncthreads();
+  if (dbg && threadIdx.x == 0) p.dbg[6] = globaltimer_ns();  // all roles done
   cluster_sync_all();  // peer finished reading its TMEM / signalling our barriers
   if (warp == 1) {
     tc_fence_after();

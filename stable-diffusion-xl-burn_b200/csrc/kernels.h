@@ -88,6 +88,8 @@ struct alignas(64) IgemmParams {
   int bias_bstride;
   const float* res;           // nullable f32 residual [pixels, ldr]
   int ldr;
+  int dbg_mode;               // diagnostics only: 1 = skip TMA loads, 2 = skip MMAs (results are garbage)
+  unsigned long long* dbg;    // nullable: per-role %globaltimer stamps of CTA 0 (tools/igemm_timeline.py)
 };
 // A operand view: NHWC f16 tensor [Bn, H, W, C] with channel pitch `pitch` (elements, multiple of 8).
 int make_tmap_act(CUtensorMap* tm, const __half* base, int Bn, int H, int W, int C, int pitch, int Wt,
