@@ -319,7 +319,7 @@ struct Loader {
 };
 
 static int geglu_bn_for(int n_out /*4C*/) {
-  for (int hb = 128; hb >= 16; hb >>= 1)
+  for (int hb = 128; hb >= 32; hb >>= 1)
     if (n_out % hb == 0) return 2 * hb;
   return 0;
 }

@@ -62,123 +62,166 @@ __device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
                : "memory");
 }
 
-// Residual prefetch for one 16-column chunk (4 x float4 per thread). Issued one chunk ahead of its use (and, for the
-// first chunk of a tile, before the accumulator is even complete) so the L2 latency hides under TMEM loads / MMAs.
-struct ResChunk { float4 v[4]; };
-__device__ __forceinline__ ResChunk prefetch_res(const IgemmParams& p, bool row_ok, size_t pix, int n) {
-  ResChunk r;
-  if (p.res != nullptr && row_ok && n + 16 <= p.N) {
-    const float4* src = reinterpret_cast<const float4*>(p.res + pix * p.ldr + n);
+// ------------------------------------------------------------------------------------------------
+// Epilogue. TMEM hands every thread one accumulator ROW (lane = row), which is the worst possible shape for global
+// memory (32 rows per warp instruction). Each epilogue warp therefore transposes 32x32-column blocks through a private
+// smem staging buffer (row pitch 36 words: conflict-free for 128-bit row-wise writes and column-group reads) and does
+// all residual loads / output stores with lanes running along the contiguous N dimension: 4 fully used 128 B lines per
+// warp instruction instead of 32 partial ones.
+//   LINEAR: out = acc + bias[batch] (+ f32 residual), f32 or f16.   GEGLU: out = value * gelu_erf(gate), f16.
+// ------------------------------------------------------------------------------------------------
+static constexpr int kStagePitch = 36;                                   // words
+static constexpr int kStageBytesPerWarp = 32 * kStagePitch * 4;           // 4608 B
+static constexpr int kEpiStageBytes = kEpiWarps * kStageBytesPerWarp;     // 36864 B
+
+struct EpiRow {          // per-lane description of "my" accumulator row (lane = row within the warp's 32 rows)
+  size_t pix;            // pixel (row of the output matrix)
+  bool ok;               // inside the image / batch
+  int bb;                // batch index (selects the bias row)
+};
+
+// one 32-column block (or a 16-column tail when ncols == 16) of the LINEAR epilogue
+__device__ __forceinline__ void epi_linear_block(const IgemmParams& p, float* stage, uint32_t taddr, int n, int ncols,
+                                                 const EpiRow& me, uint32_t ok_mask, int lane) {
+  // ---- phase 1: TMEM -> registers (+bias) -> smem, lane = row
+  uint32_t v[32];
+  if (ncols == 32) tmem_ld32(taddr, v);
+  else {
+    uint32_t t[16];
+    tmem_ld16(taddr, t);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) r.v[i] = src[i];
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) r.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < 16; ++i) { v[i] = t[i]; v[16 + i] = 0u; }
   }
-  return r;
+  const float* bias = p.bias ? p.bias + (size_t)me.bb * p.bias_bstride + n : nullptr;
+  tmem_ld_wait();
+  float* myrow = stage + lane * kStagePitch;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float4 f = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                           __uint_as_float(v[4 * i + 3]));
+    if (bias != nullptr && 4 * i < ncols && n + 4 * i < p.N) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias) + i);
+      f.x += b4.x; f.y += b4.y; f.z += b4.z; f.w += b4.w;
+    }
+    *reinterpret_cast<float4*>(myrow + 4 * i) = f;
+  }
+  __syncwarp();
+  // ---- phase 2: lanes run along N: 8 lanes x float4 per row, 4 rows per instruction
+  const int rr = lane >> 3, c4 = (lane & 7) << 2;
+  const bool col_ok = c4 < ncols && n + c4 < p.N;
+  const uint32_t pix_lo = (uint32_t)me.pix, pix_hi = (uint32_t)(me.pix >> 32);
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int row = it * 4 + rr;
+    const size_t pix = ((size_t)__shfl_sync(0xffffffffu, pix_hi, row) << 32) | __shfl_sync(0xffffffffu, pix_lo, row);
+    if (((ok_mask >> row) & 1u) && col_ok) {
+      float4 f = *reinterpret_cast<const float4*>(stage + row * kStagePitch + c4);
+      if (p.res != nullptr) {
+        const float4 r4 = *reinterpret_cast<const float4*>(p.res + pix * p.ldr + n + c4);
+        f.x += r4.x; f.y += r4.y; f.z += r4.z; f.w += r4.w;
+      }
+      if (p.out_f32) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.ldo + n + c4) = f;
+      } else {
+        __half2 a = __floats2half2_rn(f.x, f.y), b = __floats2half2_rn(f.z, f.w);
+        uint2 o;
+        o.x = *reinterpret_cast<uint32_t*>(&a);
+        o.y = *reinterpret_cast<uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + pix * p.ldo + n + c4) = o;
+      }
+    }
+  }
+  __syncwarp();
 }
 
-// Epilogue of one 128 x BN accumulator tile for the calling thread's row (TMEM lane): column chunks
-// [c_begin, c_end) of 16. LINEAR: out = acc + bias[b] (+ f32 residual) as f32 or f16. GEGLU: out = value*gelu(gate).
-// `rfirst` is the already-prefetched residual of chunk c_begin (LINEAR only).
-__device__ __forceinline__ void epilogue_tile(const IgemmParams& p, uint32_t trow, int nt, int n0, bool row_ok, size_t pix,
-                                              int bb, int c_begin, int c_end, ResChunk rfirst) {
+// GEGLU block: 32 value columns at taddr_v, the matching 32 gate columns at taddr_g -> 32 f16 outputs
+__device__ __forceinline__ void epi_geglu_block(const IgemmParams& p, float* stage, uint32_t taddr_v, uint32_t taddr_g, int nv,
+                                                int ng, int ncol_out, const EpiRow& me, uint32_t ok_mask, int lane) {
+  uint32_t v[32], g[32];
+  tmem_ld32(taddr_v, v);
+  tmem_ld32(taddr_g, g);
+  tmem_ld_wait();
+  float* myrow = stage + lane * kStagePitch;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float4 x = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                           __uint_as_float(v[4 * i + 3]));
+    float4 y = make_float4(__uint_as_float(g[4 * i]), __uint_as_float(g[4 * i + 1]), __uint_as_float(g[4 * i + 2]),
+                           __uint_as_float(g[4 * i + 3]));
+    if (p.bias != nullptr) {
+      const float4 bx = __ldg(reinterpret_cast<const float4*>(p.bias + nv) + i);
+      const float4 by = __ldg(reinterpret_cast<const float4*>(p.bias + ng) + i);
+      x.x += bx.x; x.y += bx.y; x.z += bx.z; x.w += bx.w;
+      y.x += by.x; y.y += by.y; y.z += by.z; y.w += by.w;
+    }
+    *reinterpret_cast<float4*>(myrow + 4 * i) =
+        make_float4(x.x * gelu_erf_f(y.x), x.y * gelu_erf_f(y.y), x.z * gelu_erf_f(y.z), x.w * gelu_erf_f(y.w));
+  }
+  __syncwarp();
+  const int rr = lane >> 3, c4 = (lane & 7) << 2;
+  const uint32_t pix_lo = (uint32_t)me.pix, pix_hi = (uint32_t)(me.pix >> 32);
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int row = it * 4 + rr;
+    const size_t pix = ((size_t)__shfl_sync(0xffffffffu, pix_hi, row) << 32) | __shfl_sync(0xffffffffu, pix_lo, row);
+    if ((ok_mask >> row) & 1u) {
+      const float4 f = *reinterpret_cast<const float4*>(stage + row * kStagePitch + c4);
+      __half2 a = __floats2half2_rn(f.x, f.y), b = __floats2half2_rn(f.z, f.w);
+      uint2 o;
+      o.x = *reinterpret_cast<uint32_t*>(&a);
+      o.y = *reinterpret_cast<uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + pix * p.ldo + ncol_out + c4) = o;
+    }
+  }
+  __syncwarp();
+}
+
+// Epilogue of one 128 x BN accumulator tile for one warp (32 rows, `half` selects which column blocks it owns).
+__device__ __forceinline__ void epilogue_tile(const IgemmParams& p, float* stage, uint32_t trow, int nt, int n0,
+                                              const EpiRow& me, int half, int lane) {
   const int BN = p.BN;
+  const uint32_t ok_mask = __ballot_sync(0xffffffffu, me.ok);
   if (p.mode == IGEMM_LINEAR) {
-    const float* bias = p.bias ? p.bias + (size_t)bb * p.bias_bstride : nullptr;
-    ResChunk rcur = rfirst;
-    for (int ch = c_begin; ch < c_end; ++ch) {
-      const int c = ch << 4;
-      uint32_t v[16];
-      tmem_ld16(trow + c, v);
-      const int n = n0 + c;
-      // next chunk's residual and this chunk's bias are in flight while the TMEM load completes
-      ResChunk rnext = (ch + 1 < c_end) ? prefetch_res(p, row_ok, pix, n + 16) : rcur;
-      float4 b4[4];
-      const bool full = row_ok && (n + 16 <= p.N);
-      if (bias != nullptr && full) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) b4[i] = __ldg(reinterpret_cast<const float4*>(bias + n) + i);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) b4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((p.N & 15) == 0) {
+      // column blocks of 32 (+ one 16-wide tail when BN % 32 == 16), split between the two warps of a lane quarter
+      const int nb = (BN + 31) >> 5;
+      const int b0 = half == 0 ? 0 : ((nb + 1) >> 1), b1 = half == 0 ? ((nb + 1) >> 1) : nb;
+      for (int bI = b0; bI < b1; ++bI) {
+        const int c = bI << 5;
+        const int ncols = (BN - c) >= 32 ? 32 : 16;
+        if (n0 + c < p.N) epi_linear_block(p, stage, trow + c, n0 + c, ncols, me, ok_mask, lane);
       }
-      tmem_ld_wait();
-      if (full) {
-        float f[16];
+    } else if (half == 0) {
+      // ragged N (e.g. the 320->4 output conv): scalar, guarded, row-per-thread
+      const float* bias = p.bias ? p.bias + (size_t)me.bb * p.bias_bstride : nullptr;
+      const float* res = p.res ? p.res + me.pix * p.ldr : nullptr;
+      for (int c = 0; c < BN; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(trow + c, v);
+        tmem_ld_wait();
+        const int n = n0 + c;
+        if (me.ok) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b4[i].x + rcur.v[i].x;
-          f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4[i].y + rcur.v[i].y;
-          f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4[i].z + rcur.v[i].z;
-          f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4[i].w + rcur.v[i].w;
-        }
-        if (p.out_f32) {
-          float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.ldo + n);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) o[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-        } else {
-          __half* o = reinterpret_cast<__half*>(p.out) + pix * p.ldo + n;
-          uint32_t h[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            __half2 t = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
-            h[i] = *reinterpret_cast<uint32_t*>(&t);
-          }
-          *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
-          *reinterpret_cast<uint4*>(o + 8) = make_uint4(h[4], h[5], h[6], h[7]);
-        }
-      } else if (row_ok && n < p.N) {
-        // ragged N tail (e.g. the 320->4 output conv): scalar, guarded
-        const float* res = p.res ? p.res + pix * p.ldr : nullptr;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          if (n + i < p.N) {
-            float x = __uint_as_float(v[i]);
-            if (bias) x += bias[n + i];
-            if (res) x += res[n + i];
-            if (p.out_f32) reinterpret_cast<float*>(p.out)[pix * p.ldo + n + i] = x;
-            else reinterpret_cast<__half*>(p.out)[pix * p.ldo + n + i] = __float2half_rn(x);
+          for (int i = 0; i < 16; ++i) {
+            if (n + i < p.N) {
+              float x = __uint_as_float(v[i]);
+              if (bias) x += bias[n + i];
+              if (res) x += res[n + i];
+              if (p.out_f32) reinterpret_cast<float*>(p.out)[me.pix * p.ldo + n + i] = x;
+              else reinterpret_cast<__half*>(p.out)[me.pix * p.ldo + n + i] = __float2half_rn(x);
+            }
           }
         }
       }
-      rcur = rnext;
     }
   } else {
     // GEGLU (reference unet/mod.rs:942-956): tile columns [0,BN/2) = value, [BN/2,BN) = matching gate
     const int hb = BN >> 1;
-    __half* o = reinterpret_cast<__half*>(p.out) + pix * p.ldo + (size_t)nt * hb;
-    for (int ch = c_begin; ch < c_end; ++ch) {
-      const int c = ch << 4;
-      uint32_t v[16], g[16];
-      tmem_ld16(trow + c, v);
-      tmem_ld16(trow + hb + c, g);
-      float4 bv[4], bg[4];
-      if (p.bias != nullptr) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          bv[i] = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c) + i);
-          bg[i] = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + hb + c) + i);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) bv[i] = bg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      tmem_ld_wait();
-      if (row_ok && n0 + c < p.N) {
-        const float* fbv = reinterpret_cast<const float*>(bv);
-        const float* fbg = reinterpret_cast<const float*>(bg);
-        uint32_t h[8];
-#pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          const float x0 = __uint_as_float(v[i]) + fbv[i], x1 = __uint_as_float(v[i + 1]) + fbv[i + 1];
-          const float g0 = __uint_as_float(g[i]) + fbg[i], g1 = __uint_as_float(g[i + 1]) + fbg[i + 1];
-          __half2 t = __floats2half2_rn(x0 * gelu_erf_f(g0), x1 * gelu_erf_f(g1));
-          h[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
-        }
-        *reinterpret_cast<uint4*>(o + c) = make_uint4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<uint4*>(o + c + 8) = make_uint4(h[4], h[5], h[6], h[7]);
-      }
+    const int nb = hb >> 5;  // hb is a multiple of 32 (geglu_bn_for)
+    const int b0 = half == 0 ? 0 : ((nb + 1) >> 1), b1 = half == 0 ? ((nb + 1) >> 1) : nb;
+    for (int bI = b0; bI < b1; ++bI) {
+      const int c = bI << 5;
+      epi_geglu_block(p, stage, trow + c, trow + hb + c, n0 + c, n0 + hb + c, nt * hb + c, me, ok_mask, lane);
     }
   }
 }
@@ -195,6 +238,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   uint64_t* tmem_full = empty_bar + nst;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;    // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* epi_stage = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tmem_ptr) + 16);  // [kEpiWarps][32][36] f32
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -325,14 +369,12 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   } else {
     // ===================== epilogue warps (2..9) =====================
     const int q = warp & 3;               // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;     // which half of the tile's column chunks
+    const int half = (warp - 2) >> 2;     // which half of the tile's column blocks
     const int r = q * 32 + lane;          // tile row == TMEM lane
     const int wt = r % p.Wt;
     const int ht = (r / p.Wt) % p.Ht;
     const int bt = r / (p.Wt * p.Ht);
-    const int nchunks = (p.mode == IGEMM_LINEAR ? BN : (BN >> 1)) >> 4;
-    const int c_begin = half == 0 ? 0 : ((nchunks + 1) >> 1);
-    const int c_end = half == 0 ? ((nchunks + 1) >> 1) : nchunks;
+    float* stage_buf = epi_stage + (warp - 2) * (32 * kStagePitch);
     int lt = 0;
     for (int st = cluster_id; st < num_super; st += num_clusters, ++lt) {
       const int mt = (st % m_super) * CM + cm_idx, nt = (st / m_super) * CN + cn_idx;
@@ -340,19 +382,18 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       const int th = (mt / p.tilesW) % p.tilesH;
       const int tb = mt / (p.tilesW * p.tilesH);
       const int bb = tb * p.Bt + bt, hh = th * p.Ht + ht, ww = tw * p.Wt + wt;
-      const int n0 = nt * BN;
-      const bool row_ok = (bb < p.Bn) && (hh < p.H) && (ww < p.W);
-      const size_t pix = ((size_t)bb * p.H + hh) * p.W + ww;
+      EpiRow me;
+      me.ok = (bb < p.Bn) && (hh < p.H) && (ww < p.W);
+      me.pix = me.ok ? ((size_t)bb * p.H + hh) * p.W + ww : 0;
+      me.bb = me.ok ? bb : 0;
       const int buf = lt & 1;
-      const ResChunk rfirst = prefetch_res(p, row_ok, pix, n0 + (c_begin << 4));
       mbar_wait(&tmem_full[buf], (lt >> 1) & 1);
       if (dbg && lt == 0 && threadIdx.x == 64) p.dbg[3] = globaltimer_ns();  // first accumulator complete
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
-
-      epilogue_tile(p, trow, nt, n0, row_ok, pix, bb, c_begin, c_end, rfirst);
-      // all TMEM reads of this buffer are complete (tcgen05.wait::ld above): hand it back to the MMA warp
+      epilogue_tile(p, stage_buf, trow, nt, nt * BN, me, half, lane);
       if (dbg && lt == 0 && threadIdx.x == 64) p.dbg[4] = globaltimer_ns();  // first epilogue done
+      // all TMEM reads of this buffer are complete (tcgen05.wait::ld above): hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
@@ -442,6 +483,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_pair_kernel(const __grid_co
   uint64_t* tmem_full = empty_bar + nst;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;    // [2]  (used in the leader)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* epi_stage = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tmem_ptr) + 16);  // [kEpiWarps][32][36] f32
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -563,9 +605,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_pair_kernel(const __grid_co
     const int wt = r % p.Wt;
     const int ht = (r / p.Wt) % p.Ht;
     const int bt = r / (p.Wt * p.Ht);
-    const int nchunks = (p.mode == IGEMM_LINEAR ? BN : (BN >> 1)) >> 4;
-    const int c_begin = half == 0 ? 0 : ((nchunks + 1) >> 1);
-    const int c_end = half == 0 ? ((nchunks + 1) >> 1) : nchunks;
+    float* stage_buf = epi_stage + (warp - 2) * (32 * kStagePitch);
     int lt = 0;
     for (int pt = pair_id; pt < num_ptiles; pt += num_pairs, ++lt) {
       const int mt = (pt % pm_tiles) * 2 + rank, nt = pt / pm_tiles;
@@ -573,16 +613,16 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_pair_kernel(const __grid_co
       const int th = (mt / p.tilesW) % p.tilesH;
       const int tb = mt / (p.tilesW * p.tilesH);
       const int bb = tb * p.Bt + bt, hh = th * p.Ht + ht, ww = tw * p.Wt + wt;
-      const int n0 = nt * BN;
-      const bool row_ok = (bb < p.Bn) && (hh < p.H) && (ww < p.W);
-      const size_t pix = ((size_t)bb * p.H + hh) * p.W + ww;
+      EpiRow me;
+      me.ok = (bb < p.Bn) && (hh < p.H) && (ww < p.W);
+      me.pix = me.ok ? ((size_t)bb * p.H + hh) * p.W + ww : 0;
+      me.bb = me.ok ? bb : 0;
       const int buf = lt & 1;
-      const ResChunk rfirst = prefetch_res(p, row_ok, pix, n0 + (c_begin << 4));
       mbar_wait(&tmem_full[buf], (lt >> 1) & 1);
       if (dbg && lt == 0 && threadIdx.x == 64) p.dbg[3] = globaltimer_ns();  // first accumulator complete
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
-      epilogue_tile(p, trow, nt, n0, row_ok, pix, bb, c_begin, c_end, rfirst);
+      epilogue_tile(p, stage_buf, trow, nt, nt * BN, me, half, lane);
       if (dbg && lt == 0 && threadIdx.x == 64) p.dbg[4] = globaltimer_ns();  // first epilogue done
       tc_fence_before();
       __syncwarp();
@@ -716,7 +756,7 @@ static int device_sms() {
 }
 
 static size_t igemm_smem_bytes(int nst, int b_rows) {
-  return (size_t)nst * (kABytes + b_rows * 128) + 1024 /*align slack*/ + (2 * nst + 4) * 8 + 16;
+  return (size_t)nst * (kABytes + b_rows * 128) + 1024 /*align slack*/ + (2 * nst + 4) * 8 + 32 + kEpiStageBytes;
 }
 
 int igemm_configure(IgemmParams& p, const IgemmOperands& o, int outW, int outH, int outB, int mode, int geglu_bn) {
@@ -761,7 +801,7 @@ int igemm_configure(IgemmParams& p, const IgemmOperands& o, int outW, int outH, 
   if (!r) r = make_tmap_wgt(&p.tmB, o.w, o.N, o.Ktot, p.BN / CM);
   if (r) return r;
   const int stage_bytes = kABytes + (p.pair ? p.BN * 64 : p.BN * 128);
-  int nst = (224 * 1024) / stage_bytes;
+  int nst = (226 * 1024 - 1024 - 256 - kEpiStageBytes) / stage_bytes;
   if (nst > 8) nst = 8;
   if (nst < 2) nst = 2;
   p.nstages = nst;
