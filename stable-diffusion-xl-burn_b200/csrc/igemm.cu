@@ -80,10 +80,39 @@ struct EpiRow {          // per-lane description of "my" accumulator row (lane =
   int bb;                // batch index (selects the bias row)
 };
 
-// one 32-column block (or a 16-column tail when ncols == 16) of the LINEAR epilogue
+// Global operands of one LINEAR block in the phase-2 (lanes-along-N) mapping, loaded ahead of use: lane handles
+// rows it*4 + (lane>>3), it = 0..7, columns c4 = (lane&7)*4 .. +3 of the block.
+struct EpiPrefetch {
+  float4 res[8];
+  float4 bias;            // valid when all rows of the warp share one batch (EpiRows::bb_uniform)
+};
+struct EpiRows {          // phase-2 per-lane row descriptors (constant for the whole tile)
+  size_t pix[8];
+  int bb[8];
+  uint32_t ok;            // bit it: row valid
+  bool bb_uniform;        // warp-uniform: every valid row has batch bb[0]-equivalent (bias row shared)
+  int bb0;
+};
+__device__ __forceinline__ EpiPrefetch epi_prefetch(const IgemmParams& p, const EpiRows& rows, int n, int ncols, int lane) {
+  EpiPrefetch f;
+  const int c4 = (lane & 7) << 2;
+  const bool col_ok = c4 < ncols && n + c4 < p.N;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const bool ok = ((rows.ok >> it) & 1u) && col_ok;
+    f.res[it] = (ok && p.res != nullptr) ? *reinterpret_cast<const float4*>(p.res + rows.pix[it] * p.ldr + n + c4)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  f.bias = (col_ok && p.bias != nullptr && rows.bb_uniform)
+               ? __ldg(reinterpret_cast<const float4*>(p.bias + (size_t)rows.bb0 * p.bias_bstride + n + c4))
+               : make_float4(0.f, 0.f, 0.f, 0.f);
+  return f;
+}
+
+// one 32-column block (or a 16-column tail when ncols == 16) of the LINEAR epilogue; `pf` was issued earlier
 __device__ __forceinline__ void epi_linear_block(const IgemmParams& p, float* stage, uint32_t taddr, int n, int ncols,
-                                                 const EpiRow& me, uint32_t ok_mask, int lane) {
-  // ---- phase 1: TMEM -> registers (+bias) -> smem, lane = row
+                                                 const EpiRows& rows, const EpiPrefetch& pf, int lane) {
+  // ---- phase 1: TMEM -> registers -> smem, lane = row
   uint32_t v[32];
   if (ncols == 32) tmem_ld32(taddr, v);
   else {
@@ -92,34 +121,28 @@ __device__ __forceinline__ void epi_linear_block(const IgemmParams& p, float* st
 #pragma unroll
     for (int i = 0; i < 16; ++i) { v[i] = t[i]; v[16 + i] = 0u; }
   }
-  const float* bias = p.bias ? p.bias + (size_t)me.bb * p.bias_bstride + n : nullptr;
   tmem_ld_wait();
   float* myrow = stage + lane * kStagePitch;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float4 f = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
-                           __uint_as_float(v[4 * i + 3]));
-    if (bias != nullptr && 4 * i < ncols && n + 4 * i < p.N) {
-      const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias) + i);
-      f.x += b4.x; f.y += b4.y; f.z += b4.z; f.w += b4.w;
-    }
-    *reinterpret_cast<float4*>(myrow + 4 * i) = f;
-  }
+  for (int i = 0; i < 8; ++i)
+    *reinterpret_cast<uint4*>(myrow + 4 * i) = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
   __syncwarp();
   // ---- phase 2: lanes run along N: 8 lanes x float4 per row, 4 rows per instruction
   const int rr = lane >> 3, c4 = (lane & 7) << 2;
   const bool col_ok = c4 < ncols && n + c4 < p.N;
-  const uint32_t pix_lo = (uint32_t)me.pix, pix_hi = (uint32_t)(me.pix >> 32);
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int row = it * 4 + rr;
-    const size_t pix = ((size_t)__shfl_sync(0xffffffffu, pix_hi, row) << 32) | __shfl_sync(0xffffffffu, pix_lo, row);
-    if (((ok_mask >> row) & 1u) && col_ok) {
+    if (((rows.ok >> it) & 1u) && col_ok) {
       float4 f = *reinterpret_cast<const float4*>(stage + row * kStagePitch + c4);
-      if (p.res != nullptr) {
-        const float4 r4 = *reinterpret_cast<const float4*>(p.res + pix * p.ldr + n + c4);
-        f.x += r4.x; f.y += r4.y; f.z += r4.z; f.w += r4.w;
-      }
+      float4 b4 = pf.bias;
+      if (!rows.bb_uniform && p.bias != nullptr)  // rows of different batches in one warp tile (tiny images only)
+        b4 = __ldg(reinterpret_cast<const float4*>(p.bias + (size_t)rows.bb[it] * p.bias_bstride + n + c4));
+      f.x += b4.x + pf.res[it].x;
+      f.y += b4.y + pf.res[it].y;
+      f.z += b4.z + pf.res[it].z;
+      f.w += b4.w + pf.res[it].w;
+      const size_t pix = rows.pix[it];
       if (p.out_f32) {
         *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.ldo + n + c4) = f;
       } else {
@@ -176,20 +199,54 @@ __device__ __forceinline__ void epi_geglu_block(const IgemmParams& p, float* sta
   __syncwarp();
 }
 
-// Epilogue of one 128 x BN accumulator tile for one warp (32 rows, `half` selects which column blocks it owns).
-__device__ __forceinline__ void epilogue_tile(const IgemmParams& p, float* stage, uint32_t trow, int nt, int n0,
-                                              const EpiRow& me, int half, int lane) {
-  const int BN = p.BN;
+// phase-2 row descriptors from the per-lane (lane = row) description
+__device__ __forceinline__ EpiRows epi_rows(const EpiRow& me, int lane) {
+  EpiRows r;
   const uint32_t ok_mask = __ballot_sync(0xffffffffu, me.ok);
+  const uint32_t pix_lo = (uint32_t)me.pix, pix_hi = (uint32_t)(me.pix >> 32);
+  const int rr = lane >> 3;
+  r.ok = 0;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int row = it * 4 + rr;
+    r.pix[it] = ((size_t)__shfl_sync(0xffffffffu, pix_hi, row) << 32) | __shfl_sync(0xffffffffu, pix_lo, row);
+    r.bb[it] = __shfl_sync(0xffffffffu, me.bb, row);
+    r.ok |= ((ok_mask >> row) & 1u) << it;
+  }
+  // batch uniformity over the warp's valid rows (lane = row view)
+  const int first = ok_mask ? (__ffs(ok_mask) - 1) : 0;
+  r.bb0 = __shfl_sync(0xffffffffu, me.bb, first);
+  r.bb_uniform = __all_sync(0xffffffffu, !me.ok || me.bb == r.bb0);
+  return r;
+}
+// column-block range [b0, b1) of this warp for a LINEAR tile
+__device__ __forceinline__ void epi_linear_range(int BN, int half, int& b0, int& b1) {
+  const int nb = (BN + 31) >> 5;
+  b0 = half == 0 ? 0 : ((nb + 1) >> 1);
+  b1 = half == 0 ? ((nb + 1) >> 1) : nb;
+}
+
+// Epilogue of one 128 x BN accumulator tile for one warp (32 rows, `half` selects which column blocks it owns).
+// `pf0` = prefetched operands of the warp's first LINEAR block (issued before the accumulator was complete).
+__device__ __forceinline__ void epilogue_tile(const IgemmParams& p, float* stage, uint32_t trow, int nt, int n0,
+                                              const EpiRow& me, const EpiRows& rows, EpiPrefetch pf0, int half, int lane) {
+  const int BN = p.BN;
   if (p.mode == IGEMM_LINEAR) {
     if ((p.N & 15) == 0) {
       // column blocks of 32 (+ one 16-wide tail when BN % 32 == 16), split between the two warps of a lane quarter
-      const int nb = (BN + 31) >> 5;
-      const int b0 = half == 0 ? 0 : ((nb + 1) >> 1), b1 = half == 0 ? ((nb + 1) >> 1) : nb;
+      int b0, b1;
+      epi_linear_range(BN, half, b0, b1);
+      EpiPrefetch pf = pf0;
       for (int bI = b0; bI < b1; ++bI) {
         const int c = bI << 5;
         const int ncols = (BN - c) >= 32 ? 32 : 16;
-        if (n0 + c < p.N) epi_linear_block(p, stage, trow + c, n0 + c, ncols, me, ok_mask, lane);
+        EpiPrefetch nxt = pf;
+        if (bI + 1 < b1) {  // next block's operands fly while this block is transposed
+          const int c2 = (bI + 1) << 5;
+          nxt = epi_prefetch(p, rows, n0 + c2, (BN - c2) >= 32 ? 32 : 16, lane);
+        }
+        if (n0 + c < p.N) epi_linear_block(p, stage, trow + c, n0 + c, ncols, rows, pf, lane);
+        pf = nxt;
       }
     } else if (half == 0) {
       // ragged N (e.g. the 320->4 output conv): scalar, guarded, row-per-thread
@@ -216,6 +273,7 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, float* stage
     }
   } else {
     // GEGLU (reference unet/mod.rs:942-956): tile columns [0,BN/2) = value, [BN/2,BN) = matching gate
+    const uint32_t ok_mask = __ballot_sync(0xffffffffu, me.ok);
     const int hb = BN >> 1;
     const int nb = hb >> 5;  // hb is a multiple of 32 (geglu_bn_for)
     const int b0 = half == 0 ? 0 : ((nb + 1) >> 1), b1 = half == 0 ? ((nb + 1) >> 1) : nb;
@@ -387,11 +445,25 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       me.pix = me.ok ? ((size_t)bb * p.H + hh) * p.W + ww : 0;
       me.bb = me.ok ? bb : 0;
       const int buf = lt & 1;
+      // row descriptors + the first block's residual/bias are fetched while the MMAs of this tile still run
+      const EpiRows rows = epi_rows(me, lane);
+      EpiPrefetch pf0;
+      {
+        int eb0, eb1;
+        epi_linear_range(BN, half, eb0, eb1);
+        const int c0 = eb0 << 5;
+        if (p.mode == IGEMM_LINEAR && (p.N & 15) == 0 && eb0 < eb1) pf0 = epi_prefetch(p, rows, nt * BN + c0, (BN - c0) >= 32 ? 32 : 16, lane);
+        else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pf0.res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          pf0.bias = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
       mbar_wait(&tmem_full[buf], (lt >> 1) & 1);
       if (dbg && lt == 0 && threadIdx.x == 64) p.dbg[3] = globaltimer_ns();  // first accumulator complete
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
-      epilogue_tile(p, stage_buf, trow, nt, nt * BN, me, half, lane);
+      epilogue_tile(p, stage_buf, trow, nt, nt * BN, me, rows, pf0, half, lane);
       if (dbg && lt == 0 && threadIdx.x == 64) p.dbg[4] = globaltimer_ns();  // first epilogue done
       // all TMEM reads of this buffer are complete (tcgen05.wait::ld above): hand it back to the MMA warp
       tc_fence_before();
@@ -618,11 +690,25 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_pair_kernel(const __grid_co
       me.pix = me.ok ? ((size_t)bb * p.H + hh) * p.W + ww : 0;
       me.bb = me.ok ? bb : 0;
       const int buf = lt & 1;
+      // row descriptors + the first block's residual/bias are fetched while the MMAs of this tile still run
+      const EpiRows rows = epi_rows(me, lane);
+      EpiPrefetch pf0;
+      {
+        int eb0, eb1;
+        epi_linear_range(BN, half, eb0, eb1);
+        const int c0 = eb0 << 5;
+        if (p.mode == IGEMM_LINEAR && (p.N & 15) == 0 && eb0 < eb1) pf0 = epi_prefetch(p, rows, nt * BN + c0, (BN - c0) >= 32 ? 32 : 16, lane);
+        else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pf0.res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          pf0.bias = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
       mbar_wait(&tmem_full[buf], (lt >> 1) & 1);
       if (dbg && lt == 0 && threadIdx.x == 64) p.dbg[3] = globaltimer_ns();  // first accumulator complete
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
-      epilogue_tile(p, stage_buf, trow, nt, nt * BN, me, half, lane);
+      epilogue_tile(p, stage_buf, trow, nt, nt * BN, me, rows, pf0, half, lane);
       if (dbg && lt == 0 && threadIdx.x == 64) p.dbg[4] = globaltimer_ns();  // first epilogue done
       tc_fence_before();
       __syncwarp();
