@@ -115,9 +115,12 @@ template <typename TIn>
 __global__ void conv_in_kernel(const TIn* __restrict__ x, int Bx, int B, int Cin, int H, int W,
                                const float* __restrict__ w, const float* __restrict__ bias, int Cout,
                                float* __restrict__ y) {
-  extern __shared__ float sw[];  // [Cout][9*Cin]
+  extern __shared__ float sw[];  // [9*Cin][Cout]  (k-major: lanes = consecutive output channels, conflict-free)
   const int kk = 9 * Cin;
-  for (int i = threadIdx.x; i < Cout * kk; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < Cout * kk; i += blockDim.x) {
+    const int co = i / kk, k = i % kk;
+    sw[k * Cout + co] = w[i];
+  }
   __syncthreads();
   const int cvec = Cout / 4;
   const long total = (long)B * H * W * cvec;
@@ -128,24 +131,21 @@ __global__ void conv_in_kernel(const TIn* __restrict__ x, int Bx, int B, int Cin
     const int hh = (int)((pix / W) % H);
     const int b = (int)(pix / ((long)W * H));
     const TIn* xb = x + (size_t)(b % Bx) * Cin * H * W;
-    float in[72];  // Cin <= 8
-    for (int kh = 0; kh < 3; ++kh)
+    float4 acc = bias ? *reinterpret_cast<const float4*>(bias + cv * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int kh = 0; kh < 3; ++kh) {
+      const int ih = hh + kh - 1;
+      if (ih < 0 || ih >= H) continue;
       for (int kw = 0; kw < 3; ++kw) {
-        const int ih = hh + kh - 1, iw = ww + kw - 1;
-        const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
-        for (int c = 0; c < Cin; ++c)
-          in[(kh * 3 + kw) * Cin + c] = ok ? (float)xb[((size_t)c * H + ih) * W + iw] : 0.f;
+        const int iw = ww + kw - 1;
+        if (iw < 0 || iw >= W) continue;
+        for (int c = 0; c < Cin; ++c) {
+          const float v = (float)xb[((size_t)c * H + ih) * W + iw];   // broadcast across the warp's channel lanes
+          const float4 wv = *reinterpret_cast<const float4*>(sw + ((kh * 3 + kw) * Cin + c) * Cout + cv * 4);
+          acc.x = fmaf(v, wv.x, acc.x); acc.y = fmaf(v, wv.y, acc.y); acc.z = fmaf(v, wv.z, acc.z); acc.w = fmaf(v, wv.w, acc.w);
+        }
       }
-    float o[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int co = cv * 4 + j;
-      float a = bias ? bias[co] : 0.f;
-      const float* wr = sw + co * kk;
-      for (int k = 0; k < kk; ++k) a = fmaf(in[k], wr[k], a);
-      o[j] = a;
     }
-    *reinterpret_cast<float4*>(y + pix * Cout + cv * 4) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(y + pix * Cout + cv * 4) = acc;
   }
 }
 int conv_in_launch_t(cudaStream_t st, const void* x, int x_f32, int Bx, int B, int Cin, int H, int W, const float* w,
@@ -158,7 +158,7 @@ int conv_in_launch_t(cudaStream_t st, const void* x, int x_f32, int Bx, int B, i
   }
   const long total = (long)B * H * W * (Cout / 4);
   int grid = cdiv(total, 256);
-  if (grid > 148 * 8) grid = 148 * 8;
+  if (grid > 148 * 4) grid = 148 * 4;
   if (x_f32)
     conv_in_kernel<float><<<grid, 256, smem, st>>>((const float*)x, Bx, B, Cin, H, W, w, bias, Cout, y);
   else

@@ -830,6 +830,24 @@ int igemm_pick_bn(int m_tiles, int N, int num_sms, bool geglu) {
   return best_bn;
 }
 
+// N tile for the 2-CTA kernel: minimise max(L2->SM delivery time, tensor time) per K block.
+//   delivery ~ pairs * 2 CTAs * (16 KB A + BN*64 B of B) at ~5500 B/clk chip-wide (measured ~10.5 TB/s),
+//   tensor   ~ waves * 2*BN clk (four M=256 x BN x 16 MMAs), waves over (#SMs/2) resident pairs.
+static int igemm_pick_bn_pair(int m_tiles, int N, int num_sms) {
+  double best = 1e30;
+  int best_bn = 0;
+  for (int bn = 256; bn >= 32; bn -= 32) {
+    if (N % bn) continue;
+    const long pairs = (long)(m_tiles / 2) * (N / bn);
+    const long waves = (pairs + num_sms / 2 - 1) / (num_sms / 2);
+    const double bw = (double)pairs * 2.0 * (16384.0 + bn * 64.0) / 5500.0;
+    const double mma = (double)waves * 2.0 * bn;
+    const double cost = (bw > mma ? bw : mma) + 40.0 * waves;  // + per-tile epilogue / pipeline refill
+    if (cost < best) { best = cost; best_bn = bn; }
+  }
+  return best_bn;
+}
+
 static int device_sms() {
   static int num_sms = 0;
   if (!num_sms) {
@@ -855,7 +873,19 @@ int igemm_configure(IgemmParams& p, const IgemmOperands& o, int outW, int outH, 
   p.N = o.N;
   p.mode = mode;
   p.BN = (mode == IGEMM_GEGLU) ? geglu_bn : igemm_pick_bn(m_tiles, o.N, device_sms(), false);
+  // 2-CTA MMA (pair along M) whenever the M tile count is even and N tiles by a multiple of 32: it is the only
+  // variant that lowers the bytes delivered per SM. SDXL_B200_PAIR=0 falls back to the 1-CTA (+multicast) kernel.
+  static const bool pair_on = !(getenv("SDXL_B200_PAIR") && getenv("SDXL_B200_PAIR")[0] == '0');
+  p.pair = 0;
+  if (pair_on && m_tiles % 2 == 0 && m_tiles >= 2) {
+    if (mode == IGEMM_GEGLU) p.pair = (p.BN % 32 == 0);
+    else {
+      const int bnp = igemm_pick_bn_pair(m_tiles, o.N, device_sms());
+      if (bnp) { p.BN = bnp; p.pair = 1; }
+    }
+  }
   p.tilesN = (mode == IGEMM_GEGLU) ? (o.N / p.BN) : ((o.N + p.BN - 1) / p.BN);
+  if ((long)m_tiles * p.tilesN < 4) p.pair = 0;
   // cluster shape: share the A tile across 2 N-tiles and the B tile across 2 M-tiles when the tile grid is even
   static const char* env = getenv("SDXL_B200_CLUSTER");  // "MxN" override, e.g. 1x1 to disable
   int CM = (m_tiles % 2 == 0) ? 2 : 1, CN = (p.tilesN % 2 == 0) ? 2 : 1;
@@ -867,10 +897,6 @@ int igemm_configure(IgemmParams& p, const IgemmOperands& o, int outW, int outH, 
       CN = (p.tilesN % en == 0) ? en : 1;
     }
   }
-  // 2-CTA MMA (pair along M) is preferred whenever the M tile count is even: it is the only variant that
-  // lowers the bytes delivered per SM. SDXL_B200_PAIR=0 falls back to the 1-CTA (+multicast) kernel.
-  static const bool pair_on = !(getenv("SDXL_B200_PAIR") && getenv("SDXL_B200_PAIR")[0] == '0');
-  p.pair = (pair_on && m_tiles % 2 == 0 && (long)m_tiles * p.tilesN >= 4 && p.BN % 32 == 0) ? 1 : 0;
   if (p.pair) { CM = 2; CN = 1; }
   p.CM = CM; p.CN = CN;
   // A slice (128/CN rows): split the slowest tile dimension that is >= CN

@@ -70,20 +70,28 @@ __global__ void gn_apply_kernel(const float* __restrict__ x1, int C1, const floa
   float* rstd = mean + n_group;
   const int b = blockIdx.y;
   const int cpg = C / n_group;
-  if (threadIdx.x < n_group) {
-    const int g = threadIdx.x;
+  // finalize the statistics: 8 lanes per group walk the chunk partials (fixed order => deterministic)
+  for (int g = threadIdx.x >> 3; g < n_group; g += blockDim.x >> 3) {
+    const int sub = threadIdx.x & 7;
     double S = 0.0, Q = 0.0;
-    for (int k = 0; k < nchunk; ++k) {
-      const float* e = partial + (((size_t)b * nchunk + k) * n_group + g) * 2;
-      S += (double)e[0];
-      Q += (double)e[1];
+    for (int k = sub; k < nchunk; k += 8) {
+      const float2 e = *reinterpret_cast<const float2*>(partial + (((size_t)b * nchunk + k) * n_group + g) * 2);
+      S += (double)e.x;
+      Q += (double)e.y;
     }
-    const double n = (double)cpg * HW;
-    const double m = S / n;
-    double var = Q / n - m * m;
-    if (var < 0.0) var = 0.0;
-    mean[g] = (float)m;
-    rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      S += __shfl_xor_sync(0xffffffffu, S, o);
+      Q += __shfl_xor_sync(0xffffffffu, Q, o);
+    }
+    if (sub == 0) {
+      const double n = (double)cpg * HW;
+      const double m = S / n;
+      double var = Q / n - m * m;
+      if (var < 0.0) var = 0.0;
+      mean[g] = (float)m;
+      rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+    }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
