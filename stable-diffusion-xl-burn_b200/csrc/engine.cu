@@ -1580,13 +1580,13 @@ extern "C" int sdxl_dbg_igemm_timeline(sdxl_ctx* c, int M, int K, int N, int geg
   float* bias = (float*)T.get((size_t)N * 4);
   float* res = (float*)T.get((size_t)M * N * 4);
   void* out = T.get((size_t)M * N * 4);
-  unsigned long long* dbg = (unsigned long long*)T.get(8 * 8);
+  unsigned long long* dbg = (unsigned long long*)T.get(16 * 8);
   if (!x || !w || !bias || !res || !out || !dbg) return fail(c, 5400, "temporary allocation failed");
   CU(c, cudaMemsetAsync(x, 0, (size_t)M * K * 2, c->stream));
   CU(c, cudaMemsetAsync(w, 0, (size_t)N * Kpad * 2, c->stream));
   CU(c, cudaMemsetAsync(bias, 0, (size_t)N * 4, c->stream));
   CU(c, cudaMemsetAsync(res, 0, (size_t)M * N * 4, c->stream));
-  CU(c, cudaMemsetAsync(dbg, 0, 64, c->stream));
+  CU(c, cudaMemsetAsync(dbg, 0, 128, c->stream));
   IgemmParams p{};
   p.nseg = 1;
   p.seg[0] = {0, 0, 0, 0, Kpad / 64};
@@ -1606,10 +1606,14 @@ extern "C" int sdxl_dbg_igemm_timeline(sdxl_ctx* c, int M, int K, int N, int geg
   CU(c, cudaEventRecord(e0, c->stream));
   KL(c, igemm_launch(c->stream, p));
   CU(c, cudaEventRecord(e1, c->stream));
-  CU(c, cudaMemcpyAsync(stamps_host, dbg, 56, cudaMemcpyDeviceToHost, c->stream));
+  unsigned long long hostbuf[16];
+  CU(c, cudaMemcpyAsync(hostbuf, dbg, 128, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
   float ms = 0;
   cudaEventElapsedTime(&ms, e0, e1);
+  for (int i = 0; i < 7; ++i) stamps_host[i] = hostbuf[i];
+  fprintf(stderr, "  epi block0: tmem_ld %llu ns, st.shared+sync %llu ns, phase2 %llu ns (since acc ready: %llu)\n",
+          hostbuf[10] - hostbuf[9], hostbuf[11] - hostbuf[10], hostbuf[12] - hostbuf[11], hostbuf[9] - hostbuf[3]);
   stamps_host[7] = (uint64_t)(ms * 1e6);
   stamps_host[8] = (uint64_t)p.BN | ((uint64_t)p.pair << 16) | ((uint64_t)p.CM << 20) | ((uint64_t)p.CN << 24) | ((uint64_t)p.nstages << 28);
   cudaEventDestroy(e0);
