@@ -837,19 +837,24 @@ int igemm_pick_bn(int m_tiles, int N, int num_sms, bool geglu) {
   return best_bn;
 }
 
-// N tile for the 2-CTA kernel: minimise max(L2->SM delivery time, tensor time) per K block.
-//   delivery ~ pairs * 2 CTAs * (16 KB A + BN*64 B of B) at ~5500 B/clk chip-wide (measured ~10.5 TB/s),
-//   tensor   ~ waves * 2*BN clk (four M=256 x BN x 16 MMAs), waves over (#SMs/2) resident pairs.
-static int igemm_pick_bn_pair(int m_tiles, int N, int num_sms) {
+// N tile for the 2-CTA kernel. Measured model (tools/igemm_timeline.py, B200): one 64-deep K block costs
+// max(~610 clk issue floor, 2*BN clk tensor time, delivery at ~5500 B/clk chip-wide); the epilogue of a tile costs
+// ~2600 clk per 32-column block per warp (two warps share a lane quarter) and is exposed once per CTA.
+static int igemm_pick_bn_pair(int m_tiles, int N, int kblocks, int num_sms) {
   double best = 1e30;
   int best_bn = 0;
   for (int bn = 256; bn >= 32; bn -= 32) {
     if (N % bn) continue;
     const long pairs = (long)(m_tiles / 2) * (N / bn);
-    const long waves = (pairs + num_sms / 2 - 1) / (num_sms / 2);
-    const double bw = (double)pairs * 2.0 * (16384.0 + bn * 64.0) / 5500.0;
-    const double mma = (double)waves * 2.0 * bn;
-    const double cost = (bw > mma ? bw : mma) + 40.0 * waves;  // + per-tile epilogue / pipeline refill
+    const long slots = num_sms / 2;
+    const long waves = (pairs + slots - 1) / slots;
+    const long active = pairs < slots ? pairs : slots;
+    double per_kb = 610.0;
+    if (2.0 * bn > per_kb) per_kb = 2.0 * bn;
+    const double bw = (double)active * 2.0 * (16384.0 + bn * 64.0) / 5500.0;
+    if (bw > per_kb) per_kb = bw;
+    const double epi = ((bn + 31) / 32 + 1) / 2 * 2600.0;
+    const double cost = (double)waves * kblocks * per_kb + epi;
     if (cost < best) { best = cost; best_bn = bn; }
   }
   return best_bn;
@@ -871,6 +876,9 @@ static size_t igemm_smem_bytes(int nst, int b_rows) {
 }
 
 int igemm_configure(IgemmParams& p, const IgemmOperands& o, int outW, int outH, int outB, int mode, int geglu_bn) {
+  int total_kb = 0;
+  for (int s2 = 0; s2 < p.nseg; ++s2) total_kb += p.seg[s2].nkb;
+  if (total_kb < 1) total_kb = 1;
   igemm_pick_box(outW, outH, &p.Wt, &p.Ht, &p.Bt);
   p.W = outW; p.H = outH; p.Bn = outB;
   p.tilesW = (outW + p.Wt - 1) / p.Wt;
@@ -887,7 +895,7 @@ int igemm_configure(IgemmParams& p, const IgemmOperands& o, int outW, int outH, 
   if (pair_on && m_tiles % 2 == 0 && m_tiles >= 2) {
     if (mode == IGEMM_GEGLU) p.pair = (p.BN % 32 == 0);
     else {
-      const int bnp = igemm_pick_bn_pair(m_tiles, o.N, device_sms());
+      const int bnp = igemm_pick_bn_pair(m_tiles, o.N, total_kb, device_sms());
       if (bnp) { p.BN = bnp; p.pair = 1; }
     }
   }
