@@ -10,8 +10,7 @@
 // Online softmax (running max / sum, f32) lives in registers of 128 threads per tile (one query row each). The
 // per-block P V result is double-buffered in TMEM and folded into the register accumulator one block late, so
 // the softmax warps never wait for the tensor pipe in steady state and TMEM never needs a read-modify-write.
-// Warp roles (352 threads): warp0 TMA producer, warp1 / warp2 MMA issuers of tile A / B (warp1 owns TMEM),
-// warps 3..6 softmax A, warps 7..10 softmax B. The two tiles are independent pipelines that only share K/V stages.
+// Warp roles (320 threads): warp0 TMA producer, warp1 MMA issuer + TMEM owner, warps 2..5 softmax A, 6..9 softmax B.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -20,7 +19,7 @@ namespace sdxl {
 static constexpr int kTileBytes = 128 * 128;        // 128 rows x 64 halves (Q, K or V tile)
 static constexpr int kPBytes = 2 * 128 * 128;       // 128 rows x 128 keys, two 64-key swizzle panels
 static constexpr int kAttnSmem = 2 * kTileBytes + 4 * kTileBytes + 2 * kPBytes + 256;
-static constexpr int kAttnThreads = 352;
+static constexpr int kAttnThreads = 320;
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -44,10 +43,15 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
   const int nblk = (p.S + 127) / 128;
-  const int row0 = qt * 256;
-  const bool hasB = row0 + 128 < p.T;   // second tile holds at least one valid query
+  // Persistent: the (batch, head, 128-query tile) work list is split into contiguous, balanced ranges, one per
+  // CTA; inside its range a CTA takes two consecutive tiles of the same head as a ping-pong pair, a single
+  // tile otherwise (end of a head or of the range). This removes most of the wave-quantisation loss of a
+  // one-pair-per-CTA grid (e.g. 320 tiles on 148 SMs: 1 pair + 1 single instead of 2 full waves).
+  const int nqt = (p.T + 127) / 128;
+  const long total_tiles = (long)p.B * p.n_head * nqt;
+  const int t_begin = (int)(total_tiles * blockIdx.x / gridDim.x);
+  const int t_end = (int)(total_tiles * (blockIdx.x + 1) / gridDim.x);
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) {
@@ -57,15 +61,6 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
     tma_prefetch_desc(&p.tmQ);
     tma_prefetch_desc(&p.tmK);
     tma_prefetch_desc(&p.tmV);
-    mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], hasB ? 2 : 1);  // released by the MMA issuer of every active tile
-      mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
-      mbar_init(&pv_done[i], 1);
-    }
-    fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, 512);
   tc_fence_before();
@@ -74,6 +69,27 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
   const uint32_t tmem_base = *tmem_ptr;
   griddep_wait();  // PDL: the prologue above overlapped the previous kernel's tail
   griddep_launch_dependents();
+
+  for (int tile = t_begin; tile < t_end;) {
+  const int qt = tile % nqt;
+  const int head = (tile / nqt) % p.n_head;
+  const int b = tile / (nqt * p.n_head);
+  const int row0 = qt * 128;
+  const bool hasB = (qt + 1 < nqt) && (tile + 1 < t_end);   // pair with the next tile of the same head
+  tile += hasB ? 2 : 1;
+  // fresh barriers for every work item (nobody is using them here: see the __syncthreads at the loop end)
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&pv_done[i], 1);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -88,58 +104,61 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         tma_load_3d(sV + stage * kTileBytes, &p.tmV, &kv_full[stage], p.v_col0 + head * 64, j * 128, b);
       }
     }
-  } else if (warp == 1 || warp == 2) {
-    // ===================== MMA issuer of tile x (warp-uniform loop, lane 0 issues) =====================
-    const int x = warp - 1;
-    if (x == 0 || hasB) {
+  } else if (warp == 1) {
+    if (lane == 0) {
       const uint32_t idesc_qk = make_idesc_f16(128, false);
       const uint32_t idesc_pv = make_idesc_f16(64, true);
-      const uint32_t dhi = 64u | (1u << 14) | (2u << 29);             // SBO=1024B, version, SWIZZLE_128B
-      const uint32_t lo_flag = 1u << 16;                               // LBO(enc)=1
-      const uint32_t q_lo = ((smem_u32(sQ + x * kTileBytes) >> 4) & 0x3FFFu) | lo_flag;
-      const uint32_t k_lo0 = ((smem_u32(sK) >> 4) & 0x3FFFu) | lo_flag;
-      const uint32_t v_lo0 = ((smem_u32(sV) >> 4) & 0x3FFFu) | lo_flag;
-      const uint32_t p_lo = ((smem_u32(sP + x * kPBytes) >> 4) & 0x3FFFu) | lo_flag;
-      const uint32_t tS = tmem_base + x * 128;
-      const uint32_t tO = tmem_base + 256 + x * 128;
-      auto desc = [&](uint32_t lo) { return ((uint64_t)dhi << 32) | lo; };
+      const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
+      // S_x = Q_x K_j^T
+      auto issue_qk = [&](int x, int stage) {
+        const uint32_t qa = q_addr + x * kTileBytes, ka = smem_u32(sK + stage * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_f16(tmem_base + x * 128, make_sw128_desc(qa + k * 32), make_sw128_desc(ka + k * 32), idesc_qk, k > 0);
+        tc_commit(&s_full[x]);
+      };
+      // O_x[j&1] = P_x V_j
+      auto issue_pv = [&](int x, int j) {
+        const uint32_t pa = p_addr + x * kPBytes, va = smem_u32(sV + (j & 1) * kTileBytes);
+        const uint32_t d = tmem_base + 256 + x * 128 + (j & 1) * 64;
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+          tc_mma_f16(d, make_sw128_desc(pa + (t >> 2) * (128 * 128) + (t & 3) * 32), make_sw128_desc(va + t * 2048), idesc_pv,
+                     t > 0);
+        tc_commit(&pv_done[x]);
+      };
       mbar_wait(q_full, 0);
       mbar_wait(&kv_full[0], 0);
       tc_fence_after();
-      if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) tc_mma_f16(tS, desc(q_lo + 2 * k), desc(k_lo0 + 2 * k), idesc_qk, k > 0);
-        tc_commit(&s_full[x]);
-      }
-      __syncwarp();
+      issue_qk(0, 0);
+      if (hasB) issue_qk(1, 0);
       for (int j = 0; j < nblk; ++j) {
-        const uint32_t st_off = (uint32_t)(j & 1) * (kTileBytes >> 4);
-        mbar_wait(&p_full[x], j & 1);  // P_x(j) written, S_x(j) consumed
+        const bool more = j + 1 < nblk;
+        mbar_wait(&p_full[0], j & 1);  // P_A(j) written, S_A(j) consumed
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t d = tO + (j & 1) * 64;
-#pragma unroll
-          for (int t = 0; t < 8; ++t)   // P panel t>>2 (16 KB apart), 32 B per 16 keys; V: 16 key rows = 2048 B
-            tc_mma_f16(d, desc(p_lo + (t >> 2) * 1024 + (t & 3) * 2), desc(v_lo0 + st_off + t * 128), idesc_pv, t > 0);
-          tc_commit(&pv_done[x]);
-          tc_commit(&kv_empty[j & 1]);  // this tile no longer needs K_j / V_j
-        }
-        __syncwarp();
-        if (j + 1 < nblk) {
-          const uint32_t nx_off = (uint32_t)((j + 1) & 1) * (kTileBytes >> 4);
+        issue_pv(0, j);
+        if (more) {
           mbar_wait(&kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
           tc_fence_after();
-          if (lane == 0) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) tc_mma_f16(tS, desc(q_lo + 2 * k), desc(k_lo0 + nx_off + 2 * k), idesc_qk, k > 0);
-            tc_commit(&s_full[x]);
-          }
-          __syncwarp();
+          issue_qk(0, (j + 1) & 1);
         }
+        if (hasB) {
+          mbar_wait(&p_full[1], j & 1);
+          tc_fence_after();
+          issue_pv(1, j);
+        }
+        tc_commit(&kv_empty[j & 1]);  // K_j / V_j no longer needed once everything issued so far retires
+        if (more && hasB) issue_qk(1, (j + 1) & 1);
+      }
+      // drain: the last stage releases have no consumer; observe them so that no asynchronous arrival is still
+      // in flight when the barriers are re-initialised for the next work item
+      for (int s = 0; s < 2 && s < nblk; ++s) {
+        const int uses = (nblk - s + 1) >> 1;  // blocks j with (j & 1) == s
+        mbar_wait(&kv_empty[s], (uses - 1) & 1);
       }
     }
   } else {
-    const int x = (warp - 3) >> 2;  // softmax group: 0 = tile A (warps 3..6), 1 = tile B (warps 7..10)
+    const int x = (warp - 2) >> 2;  // softmax group: 0 = tile A, 1 = tile B
     if (x == 0 || hasB) {
       const int q = warp & 3;
       const int r = q * 32 + lane;  // query row in tile == TMEM lane
@@ -189,7 +208,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         const float m_new = fmaxf(m, mx);
         const float alpha = ex2_approx((m - m_new) * sl2e);
         const float mb = m_new * sl2e;
-        float sum = 0.f, sum1 = 0.f;
+        float sum = 0.f;
         // pass 2: p = exp2(s*scale - m*scale) -> f16 -> swizzled smem (A operand of the PV MMA)
 #pragma unroll 1
         for (int c = 0; c < 128; c += 32) {
@@ -205,8 +224,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
               if (kbase + c + i >= p.S) p0 = 0.f;
               if (kbase + c + i + 1 >= p.S) p1 = 0.f;
             }
-            sum += p0;
-            sum1 += p1;
+            sum += p0 + p1;
             __half2 t = __floats2half2_rn(p0, p1);
             h[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
           }
@@ -217,7 +235,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
             *reinterpret_cast<uint4*>(panel + (((ch0 + u) ^ rx) << 4)) =
                 make_uint4(h[4 * u], h[4 * u + 1], h[4 * u + 2], h[4 * u + 3]);
         }
-        l = l * alpha + (sum + sum1);
+        l = l * alpha + sum;
         m = m_new;
         fence_proxy_async_smem();
         tc_fence_before();
@@ -269,11 +287,11 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
+  __syncthreads();   // every role is done with this item's barriers, smem and TMEM
+  tc_fence_after();
+  }  // work items
+
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
 int attention_launch(cudaStream_t st, const AttnParams& p) {
@@ -283,7 +301,16 @@ int attention_launch(cudaStream_t st, const AttnParams& p) {
     if (e != cudaSuccess) return (int)e;
     attr = true;
   }
-  dim3 grid((p.T + 255) / 256, p.n_head, p.B);
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  const long tiles = (long)p.B * p.n_head * ((p.T + 127) / 128);
+  const long want = (tiles + 1) / 2;  // one pair per CTA when the machine is not full
+  dim3 grid((unsigned)(want < num_sms ? (want > 0 ? want : 1) : num_sms));
   return launch_kernel(attention_kernel, grid, dim3(kAttnThreads), (size_t)kAttnSmem, st, true, p);
 }
 
