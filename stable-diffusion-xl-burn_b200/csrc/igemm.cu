@@ -54,6 +54,58 @@ __device__ __forceinline__ void tma_load_2d_mc(void* dst, const void* tmap, uint
       "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1)
       : "memory");
 }
+// ---- warp-convergent (elect-predicated) producer operations: see common.cuh for the rationale ----
+#define SDXL_ELECT_BEGIN "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+__device__ __forceinline__ void mbar_expect_tx_elect(uint64_t* bar, uint32_t bytes) {
+  asm volatile(SDXL_ELECT_BEGIN "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_elect(uint64_t* bar) {
+  asm volatile(SDXL_ELECT_BEGIN "@e mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_elect(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(SDXL_ELECT_BEGIN
+               "@e cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n\t}"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_elect(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(SDXL_ELECT_BEGIN
+               "@e cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_mc_elect(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3,
+                                                     uint16_t mask) {
+  asm volatile(SDXL_ELECT_BEGIN
+               "@e cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, "
+               "%5, %6, %7}], [%2], %3;\n\t}"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "h"(mask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc_elect(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(SDXL_ELECT_BEGIN
+               "@e cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, "
+               "%5}], [%2], %3;\n\t}"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair_elect(uint32_t dst, const void* tmap, uint32_t leader_bar, int c0, int c1, int c2,
+                                                       int c3) {
+  asm volatile(SDXL_ELECT_BEGIN
+               "@e cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+               "%6}], [%2];\n\t}"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair_elect(uint32_t dst, const void* tmap, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(SDXL_ELECT_BEGIN
+               "@e cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+               "[%2];\n\t}"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(leader_bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+
 // arrive(1) on the mbarrier at the same smem offset in every CTA of `mask` once the issued MMAs retire
 __device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
@@ -357,8 +409,10 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    // The whole warp walks the loop (warp-uniform control flow keeps addresses in uniform registers); lane 0 issues.
+    // The whole warp walks the loop (warp-uniform control flow keeps addresses in uniform registers); one elected
+    // lane issues each TMA / barrier operation.
     uint32_t stage = 0, phase = 0;
+    const uint32_t smem_base = smem_u32(smem), full_base = smem_u32(full_bar);
     for (int st = cluster_id; st < num_super; st += num_clusters) {
       const int mt = (st % m_super) * CM + cm_idx, nt = (st / m_super) * CN + cn_idx;
       const int tw = mt % p.tilesW;
@@ -377,20 +431,20 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         const int cw = w0 + sg.dw, chh = h0 + sg.dh, cb = b0 + sg.db;
         for (int j = 0; j < sg.nkb; ++j, kcol += kBlockK) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (lane == 0) {
-            uint8_t* a_dst = smem + (size_t)stage * stage_bytes + (size_t)cn_idx * a_rows * 128;
-            uint8_t* b_dst = smem + (size_t)stage * stage_bytes + kABytes + (size_t)cm_idx * b_rows * 128;
+          {
+            const uint32_t a_dst = smem_base + stage * stage_bytes + (uint32_t)(cn_idx * a_rows * 128);
+            const uint32_t b_dst = smem_base + stage * stage_bytes + kABytes + (uint32_t)(cm_idx * b_rows * 128);
+            const uint32_t fb = full_base + stage * 8;
             if (p.dbg_mode == 1) {
-              mbar_arrive(&full_bar[stage]);
+              mbar_arrive_elect(&full_bar[stage]);
             } else {
-              mbar_expect_tx(&full_bar[stage], stage_bytes);
-              if (CN > 1) tma_load_4d_mc(a_dst, mapA, &full_bar[stage], j * kBlockK, cw, chh, cb, row_mask);
-              else tma_load_4d(a_dst, mapA, &full_bar[stage], j * kBlockK, cw, chh, cb);
-              if (CM > 1) tma_load_2d_mc(b_dst, &p.tmB, &full_bar[stage], kcol, n0, col_mask);
-              else tma_load_2d(b_dst, &p.tmB, &full_bar[stage], kcol, n0);
+              mbar_expect_tx_elect(&full_bar[stage], stage_bytes);
+              if (CN > 1) tma_load_4d_mc_elect(a_dst, mapA, fb, j * kBlockK, cw, chh, cb, row_mask);
+              else tma_load_4d_elect(a_dst, mapA, fb, j * kBlockK, cw, chh, cb);
+              if (CM > 1) tma_load_2d_mc_elect(b_dst, &p.tmB, fb, kcol, n0, col_mask);
+              else tma_load_2d_elect(b_dst, &p.tmB, fb, kcol, n0);
             }
           }
-          __syncwarp();
           if (++stage == (uint32_t)nst) { stage = 0; phase ^= 1; }
         }
       }
@@ -413,23 +467,20 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         mbar_wait(&full_bar[stage], phase);
         if (dbg && lt == 0 && kb == 0 && lane == 0) p.dbg[2] = globaltimer_ns();  // first operands landed
         tc_fence_after();
-        if (lane == 0) {
+        {
           const uint32_t a_lo = a_lo0 + stage * stage_inc, b_lo = a_lo + b_off;
           if (p.dbg_mode != 2) {
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k)
-              tc_mma_f16(d_tmem, ((uint64_t)desc_hi << 32) | (a_lo + 2 * k), ((uint64_t)desc_hi << 32) | (b_lo + 2 * k), idesc,
-                         (kb > 0 || k > 0) ? 1u : 0u);
+              tc_mma_f16_elect(d_tmem, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
           // free the smem slot (here and in every CTA whose loads land in it) once these MMAs have read it
-          if (cs > 1) tc_commit_mc(&empty_bar[stage], release_mask);
-          else tc_commit(&empty_bar[stage]);
+          if (cs > 1) tc_commit_mc_elect(&empty_bar[stage], release_mask);
+          else tc_commit_elect(&empty_bar[stage]);
         }
-        __syncwarp();
         if (++stage == (uint32_t)nst) { stage = 0; phase ^= 1; }
       }
-      if (lane == 0) tc_commit(&tmem_full[buf]);  // accumulator of this tile complete
-      __syncwarp();
+      tc_commit_elect(&tmem_full[buf]);  // accumulator of this tile complete
     }
   } else {
     // ===================== epilogue warps (2..9) =====================
@@ -607,8 +658,10 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_pair_kernel(const __grid_co
   if (dbg && threadIdx.x == 0) p.dbg[1] = globaltimer_ns();   // dependencies resolved
 
   if (warp == 0) {
-    // ===================== TMA producer (both CTAs): warp-uniform loop, lane 0 issues =====================
+    // ===================== TMA producer (both CTAs): warp-uniform loop, one elected lane issues =====================
     uint32_t stage = 0, phase = 0;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t leader_full_base = mapa_rank(smem_u32(full_bar), 0);
     for (int pt = pair_id; pt < num_ptiles; pt += num_pairs) {
       const int mt = (pt % pm_tiles) * 2 + rank, nt = pt / pm_tiles;
       const int tw = mt % p.tilesW;
@@ -623,19 +676,18 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_pair_kernel(const __grid_co
         const int cw = w0 + sg.dw, chh = h0 + sg.dh, cb = b0 + sg.db;
         for (int j = 0; j < sg.nkb; ++j, kcol += kBlockK) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (lane == 0) {
-            uint8_t* a_dst = smem + (size_t)stage * stage_bytes;
-            uint8_t* b_dst = a_dst + kABytes;
+          {
+            const uint32_t a_dst = smem_base + stage * stage_bytes;
+            const uint32_t b_dst = a_dst + kABytes;
             if (p.dbg_mode == 1) {
-              if (rank == 0) mbar_arrive(&full_bar[stage]);
+              if (rank == 0) mbar_arrive_elect(&full_bar[stage]);
             } else {
-              if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * stage_bytes);
-              const uint32_t lbar = mapa_rank(smem_u32(&full_bar[stage]), 0);
-              tma_load_4d_pair(a_dst, mapA, lbar, j * kBlockK, cw, chh, cb);
-              tma_load_2d_pair(b_dst, &p.tmB, lbar, kcol, n0);
+              if (rank == 0) mbar_expect_tx_elect(&full_bar[stage], 2 * stage_bytes);
+              const uint32_t lbar = leader_full_base + stage * 8;
+              tma_load_4d_pair_elect(a_dst, mapA, lbar, j * kBlockK, cw, chh, cb);
+              tma_load_2d_pair_elect(b_dst, &p.tmB, lbar, kcol, n0);
             }
           }
-          __syncwarp();
           if (++stage == (uint32_t)nst) { stage = 0; phase ^= 1; }
         }
       }
@@ -659,21 +711,18 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_pair_kernel(const __grid_co
           mbar_wait(&full_bar[stage], phase);
           if (dbg && lt == 0 && kb == 0 && lane == 0) p.dbg[2] = globaltimer_ns();  // first operands landed
           tc_fence_after();
-          if (lane == 0) {
+          {
             const uint32_t a_lo = a_lo0 + stage * stage_inc, b_lo = a_lo + b_off;
             if (p.dbg_mode != 2) {
 #pragma unroll
               for (int k = 0; k < kBlockK / 16; ++k)
-                tc_mma_f16_pair(d_tmem, ((uint64_t)desc_hi << 32) | (a_lo + 2 * k), ((uint64_t)desc_hi << 32) | (b_lo + 2 * k),
-                                idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                tc_mma_f16_pair_elect(d_tmem, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, (kb > 0 || k > 0) ? 1u : 0u);
             }
-            tc_commit_pair(&empty_bar[stage]);  // frees the slot in both CTAs
+            tc_commit_pair_elect(&empty_bar[stage]);  // frees the slot in both CTAs
           }
-          __syncwarp();
           if (++stage == (uint32_t)nst) { stage = 0; phase ^= 1; }
         }
-        if (lane == 0) tc_commit_pair(&tmem_full[buf]);  // accumulators (both halves) complete
-        __syncwarp();
+        tc_commit_pair_elect(&tmem_full[buf]);  // accumulators (both halves) complete
       }
     }
   } else {

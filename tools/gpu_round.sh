@@ -11,7 +11,7 @@ if [ "$2" != "noncu" ]; then
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --nvtx --nvtx-include "timed/" --csv \
   --log-file gpurun_out/launches_$R.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench_$R.log 2>&1
 echo "== launches: $(wc -l < gpurun_out/launches_$R.csv) lines"
-timeout 900 ncu --set full --clock-control none --import-source on --nvtx --nvtx-include "timed/" -k regex:igemm_kernel -s 300 -c 4 \
+timeout 900 ncu --set full --clock-control none --import-source on --nvtx --nvtx-include "timed/" -k regex:igemm_pair_kernel -s 300 -c 4 \
   -o gpurun_out/prof_igemm_$R -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_igemm_$R.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on --nvtx --nvtx-include "timed/" -k regex:attention_kernel -s 20 -c 2 \
   -o gpurun_out/prof_attn_$R -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_attn_$R.log 2>&1
