@@ -105,57 +105,60 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc_qk = make_idesc_f16(128, false);
-      const uint32_t idesc_pv = make_idesc_f16(64, true);
-      const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
-      // S_x = Q_x K_j^T
-      auto issue_qk = [&](int x, int stage) {
-        const uint32_t qa = q_addr + x * kTileBytes, ka = smem_u32(sK + stage * kTileBytes);
+    // ===================== MMA issuer: warp-convergent loop, one elected lane issues =====================
+    const uint32_t idesc_qk = make_idesc_f16(128, false);
+    const uint32_t idesc_pv = make_idesc_f16(64, true);
+    const uint32_t dhi = 64u | (1u << 14) | (2u << 29);   // SBO=1024B, version, SWIZZLE_128B
+    const uint32_t lo_flag = 1u << 16;                     // LBO(enc)=1
+    const uint32_t q_lo0 = ((smem_u32(sQ) >> 4) & 0x3FFFu) | lo_flag;
+    const uint32_t k_lo0 = ((smem_u32(sK) >> 4) & 0x3FFFu) | lo_flag;
+    const uint32_t v_lo0 = ((smem_u32(sV) >> 4) & 0x3FFFu) | lo_flag;
+    const uint32_t p_lo0 = ((smem_u32(sP) >> 4) & 0x3FFFu) | lo_flag;
+    constexpr uint32_t kTile16 = kTileBytes >> 4, kP16 = kPBytes >> 4;
+    // S_x = Q_x K_stage^T
+    auto issue_qk = [&](int x, int stage) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          tc_mma_f16(tmem_base + x * 128, make_sw128_desc(qa + k * 32), make_sw128_desc(ka + k * 32), idesc_qk, k > 0);
-        tc_commit(&s_full[x]);
-      };
-      // O_x[j&1] = P_x V_j
-      auto issue_pv = [&](int x, int j) {
-        const uint32_t pa = p_addr + x * kPBytes, va = smem_u32(sV + (j & 1) * kTileBytes);
-        const uint32_t d = tmem_base + 256 + x * 128 + (j & 1) * 64;
+      for (int k = 0; k < 4; ++k)
+        tc_mma_f16_elect(tmem_base + x * 128, q_lo0 + x * kTile16 + 2 * k, k_lo0 + stage * kTile16 + 2 * k, dhi, idesc_qk, k > 0);
+      tc_commit_elect(&s_full[x]);
+    };
+    // O_x[j&1] = P_x V_j   (P panel t>>2 is 16 KB further, 32 B per 16 keys; V: 16 key rows = 2048 B)
+    auto issue_pv = [&](int x, int j) {
+      const uint32_t d = tmem_base + 256 + x * 128 + (j & 1) * 64;
 #pragma unroll
-        for (int t = 0; t < 8; ++t)
-          tc_mma_f16(d, make_sw128_desc(pa + (t >> 2) * (128 * 128) + (t & 3) * 32), make_sw128_desc(va + t * 2048), idesc_pv,
-                     t > 0);
-        tc_commit(&pv_done[x]);
-      };
-      mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
+      for (int t = 0; t < 8; ++t)
+        tc_mma_f16_elect(d, p_lo0 + x * kP16 + (t >> 2) * 1024 + (t & 3) * 2, v_lo0 + (j & 1) * kTile16 + t * 128, dhi, idesc_pv,
+                         t > 0);
+      tc_commit_elect(&pv_done[x]);
+    };
+    mbar_wait(q_full, 0);
+    mbar_wait(&kv_full[0], 0);
+    tc_fence_after();
+    issue_qk(0, 0);
+    if (hasB) issue_qk(1, 0);
+    for (int j = 0; j < nblk; ++j) {
+      const bool more = j + 1 < nblk;
+      mbar_wait(&p_full[0], j & 1);  // P_A(j) written, S_A(j) consumed
       tc_fence_after();
-      issue_qk(0, 0);
-      if (hasB) issue_qk(1, 0);
-      for (int j = 0; j < nblk; ++j) {
-        const bool more = j + 1 < nblk;
-        mbar_wait(&p_full[0], j & 1);  // P_A(j) written, S_A(j) consumed
+      issue_pv(0, j);
+      if (more) {
+        mbar_wait(&kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
         tc_fence_after();
-        issue_pv(0, j);
-        if (more) {
-          mbar_wait(&kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
-          tc_fence_after();
-          issue_qk(0, (j + 1) & 1);
-        }
-        if (hasB) {
-          mbar_wait(&p_full[1], j & 1);
-          tc_fence_after();
-          issue_pv(1, j);
-        }
-        tc_commit(&kv_empty[j & 1]);  // K_j / V_j no longer needed once everything issued so far retires
-        if (more && hasB) issue_qk(1, (j + 1) & 1);
+        issue_qk(0, (j + 1) & 1);
       }
-      // drain: the last stage releases have no consumer; observe them so that no asynchronous arrival is still
-      // in flight when the barriers are re-initialised for the next work item
-      for (int s = 0; s < 2 && s < nblk; ++s) {
-        const int uses = (nblk - s + 1) >> 1;  // blocks j with (j & 1) == s
-        mbar_wait(&kv_empty[s], (uses - 1) & 1);
+      if (hasB) {
+        mbar_wait(&p_full[1], j & 1);
+        tc_fence_after();
+        issue_pv(1, j);
       }
+      tc_commit_elect(&kv_empty[j & 1]);  // K_j / V_j no longer needed once everything issued so far retires
+      if (more && hasB) issue_qk(1, (j + 1) & 1);
+    }
+    // drain: the last stage releases have no consumer; observe them so that no asynchronous arrival is still
+    // in flight when the barriers are re-initialised for the next work item
+    for (int s = 0; s < 2 && s < nblk; ++s) {
+      const int uses = (nblk - s + 1) >> 1;  // blocks j with (j & 1) == s
+      mbar_wait(&kv_empty[s], (uses - 1) & 1);
     }
   } else {
     const int x = (warp - 2) >> 2;  // softmax group: 0 = tile A, 1 = tile B

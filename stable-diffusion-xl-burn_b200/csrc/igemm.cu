@@ -887,7 +887,7 @@ int igemm_pick_bn(int m_tiles, int N, int num_sms, bool geglu) {
 }
 
 // N tile for the 2-CTA kernel. Measured model (tools/igemm_timeline.py, B200): one 64-deep K block costs
-// max(~610 clk issue floor, 2*BN clk tensor time, delivery at ~5500 B/clk chip-wide); the epilogue of a tile costs
+// max(~420 clk issue floor, 2*BN clk tensor time, delivery at ~9000 B/clk chip-wide); the epilogue of a tile costs
 // ~2600 clk per 32-column block per warp (two warps share a lane quarter) and is exposed once per CTA.
 static int igemm_pick_bn_pair(int m_tiles, int N, int kblocks, int num_sms) {
   double best = 1e30;
@@ -898,9 +898,9 @@ static int igemm_pick_bn_pair(int m_tiles, int N, int kblocks, int num_sms) {
     const long slots = num_sms / 2;
     const long waves = (pairs + slots - 1) / slots;
     const long active = pairs < slots ? pairs : slots;
-    double per_kb = 610.0;
+    double per_kb = 420.0;
     if (2.0 * bn > per_kb) per_kb = 2.0 * bn;
-    const double bw = (double)active * 2.0 * (16384.0 + bn * 64.0) / 5500.0;
+    const double bw = (double)active * 2.0 * (16384.0 + bn * 64.0) / 9000.0;
     if (bw > per_kb) per_kb = bw;
     const double epi = ((bn + 31) / 32 + 1) / 2 * 2600.0;
     const double cost = (double)waves * kblocks * per_kb + epi;
