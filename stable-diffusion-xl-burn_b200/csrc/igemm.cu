@@ -625,8 +625,6 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_pair_kernel(const __grid_co
 
   int total_kb = 0;
   for (int s = 0; s < p.nseg; ++s) total_kb += p.seg[s].nkb;
-  const int my_tiles = pair_id < num_ptiles ? (num_ptiles - pair_id + num_pairs - 1) / num_pairs : 0;
-  const int total_its = my_tiles * total_kb;   // K blocks this CTA pair walks in total
 
   uint32_t tmem_cols = 32;
   while (tmem_cols < (uint32_t)(2 * BN)) tmem_cols <<= 1;
@@ -661,10 +659,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_pair_kernel(const __grid_co
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs): warp-uniform loop, one elected lane issues =====================
-    // Ring slots are grouped in pairs that share one full/empty barrier (a 128-deep K step per barrier round trip):
-    // the per-K-block cost of the issue loops, not the tensor pipe, is what limits this kernel.
     uint32_t stage = 0, phase = 0;
-    int it = 0;
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t leader_full_base = mapa_rank(smem_u32(full_bar), 0);
     for (int pt = pair_id; pt < num_ptiles; pt += num_pairs) {
@@ -680,24 +675,19 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_pair_kernel(const __grid_co
         const void* mapA = sg.map ? (const void*)&p.tmA1 : (const void*)&p.tmA0;
         const int cw = w0 + sg.dw, chh = h0 + sg.dh, cb = b0 + sg.db;
         for (int j = 0; j < sg.nkb; ++j, kcol += kBlockK) {
-          const uint32_t g = stage >> 1;
-          if ((stage & 1) == 0) {
-            mbar_wait(&empty_bar[g], phase ^ 1);
-            // both CTAs' bytes of this slot pair (a single slot if this is the CTA's very last K block)
-            if (rank == 0 && p.dbg_mode != 1) mbar_expect_tx_elect(&full_bar[g], (it == total_its - 1 ? 2u : 4u) * stage_bytes);
-          }
+          mbar_wait(&empty_bar[stage], phase ^ 1);
           {
             const uint32_t a_dst = smem_base + stage * stage_bytes;
             const uint32_t b_dst = a_dst + kABytes;
             if (p.dbg_mode == 1) {
-              if (rank == 0 && ((stage & 1) == 1 || it == total_its - 1)) mbar_arrive_elect(&full_bar[g]);
+              if (rank == 0) mbar_arrive_elect(&full_bar[stage]);
             } else {
-              const uint32_t lbar = leader_full_base + g * 8;
+              if (rank == 0) mbar_expect_tx_elect(&full_bar[stage], 2 * stage_bytes);
+              const uint32_t lbar = leader_full_base + stage * 8;
               tma_load_4d_pair_elect(a_dst, mapA, lbar, j * kBlockK, cw, chh, cb);
               tma_load_2d_pair_elect(b_dst, &p.tmB, lbar, kcol, n0);
             }
           }
-          ++it;
           if (++stage == (uint32_t)nst) { stage = 0; phase ^= 1; }
         }
       }
@@ -711,19 +701,16 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_pair_kernel(const __grid_co
       const uint32_t a_lo0 = ((smem_u32(smem) >> 4) & 0x3FFFu) | (1u << 16);
       const uint32_t stage_inc = stage_bytes >> 4, b_off = kABytes >> 4;
       uint32_t stage = 0, phase = 0;
-      int lt = 0, it = 0;
+      int lt = 0;
       for (int pt = pair_id; pt < num_ptiles; pt += num_pairs, ++lt) {
         const int buf = lt & 1;
         mbar_wait(&tmem_empty[buf], ((lt >> 1) & 1) ^ 1);  // both CTAs' epilogues drained this buffer
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
-        for (int kb = 0; kb < total_kb; ++kb, ++it) {
-          const uint32_t g = stage >> 1;
-          if ((stage & 1) == 0) {
-            mbar_wait(&full_bar[g], phase);
-            if (dbg && lt == 0 && kb == 0 && lane == 0) p.dbg[2] = globaltimer_ns();  // first operands landed
-            tc_fence_after();
-          }
+        for (int kb = 0; kb < total_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          if (dbg && lt == 0 && kb == 0 && lane == 0) p.dbg[2] = globaltimer_ns();  // first operands landed
+          tc_fence_after();
           {
             const uint32_t a_lo = a_lo0 + stage * stage_inc, b_lo = a_lo + b_off;
             if (p.dbg_mode != 2) {
@@ -731,7 +718,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_pair_kernel(const __grid_co
               for (int k = 0; k < kBlockK / 16; ++k)
                 tc_mma_f16_pair_elect(d_tmem, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, (kb > 0 || k > 0) ? 1u : 0u);
             }
-            if ((stage & 1) == 1 || it == total_its - 1) tc_commit_pair_elect(&empty_bar[g]);  // frees the slot pair in both CTAs
+            tc_commit_pair_elect(&empty_bar[stage]);  // frees the slot in both CTAs
           }
           if (++stage == (uint32_t)nst) { stage = 0; phase ^= 1; }
         }
@@ -993,7 +980,6 @@ int igemm_configure(IgemmParams& p, const IgemmOperands& o, int outW, int outH, 
   int nst = (226 * 1024 - 1024 - 256 - kEpiStageBytes) / stage_bytes;
   if (nst > 8) nst = 8;
   if (nst < 2) nst = 2;
-  if (p.pair) nst &= ~1;  // the pair kernel groups ring slots two by two
   p.nstages = nst;
   return 0;
 }
