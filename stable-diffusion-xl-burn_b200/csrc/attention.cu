@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
       const uint32_t tS = tmem_base + lane_off + x * 128;
       const uint32_t tO = tmem_base + lane_off + 256 + x * 128;
       const float sl2e = p.scale_log2e;
-      float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
+      float m = -INFINITY, m_prev = -INFINITY, l = 0.f, alpha_prev = 0.f;
       float O[64];
 #pragma unroll
       for (int i = 0; i < 64; ++i) O[i] = 0.f;
@@ -185,61 +185,81 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         tc_fence_after();
         const int kbase = j * 128;
         const bool ragged = kbase + 128 > p.S;
-        // pass 1: row max over valid keys
-        float mx = -INFINITY;
+        // Reference for the exponent. Block 0: exact row max (one extra pass over S). Later blocks: the reference
+        // decided at the end of the previous block (lazy max): p = exp2((s - ref) * c) may exceed 1 (f16 P and f32
+        // sums have the head-room), and the row's running max is folded in only when it grew by more than 2^8.
+        // An overflow-safe redo (warp-uniform, practically never taken) re-runs the block with the exact max.
+        float ref = m;
+        if (j == 0) {
+          float mx = -INFINITY;
 #pragma unroll 1
-        for (int c = 0; c < 128; c += 32) {
-          uint32_t v[32];
-          tmem_ld32(tS + c, v);
-          tmem_ld_wait();
-          if (!ragged) {
-            float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;  // four short chains
+          for (int c = 0; c < 128; c += 32) {
+            uint32_t v[32];
+            tmem_ld32(tS + c, v);
+            tmem_ld_wait();
+            if (!ragged) {
+              float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;  // four short chains
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              m0 = fmaxf(m0, __uint_as_float(v[i]));
-              m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
-              m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
-              m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
+              for (int i = 0; i < 32; i += 4) {
+                m0 = fmaxf(m0, __uint_as_float(v[i]));
+                m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
+                m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
+                m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
+              }
+              mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (kbase + c + i < p.S) mx = fmaxf(mx, __uint_as_float(v[i]));
             }
-            mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (kbase + c + i < p.S) mx = fmaxf(mx, __uint_as_float(v[i]));
           }
+          ref = mx;
         }
-        const float m_new = fmaxf(m, mx);
-        const float alpha = ex2_approx((m - m_new) * sl2e);
-        const float mb = m_new * sl2e;
-        float sum = 0.f;
-        // pass 2: p = exp2(s*scale - m*scale) -> f16 -> swizzled smem (A operand of the PV MMA)
+        float alpha, sum, bmax;
+        bool redo;
+        do {
+          alpha = ex2_approx((m_prev - ref) * sl2e);   // rescale of everything accumulated so far (0 for block 0)
+          const float mb = ref * sl2e;
+          sum = 0.f;
+          float b0 = -INFINITY, b1 = -INFINITY;
+          // p = exp2(s*scale - ref*scale) -> f16 -> swizzled smem (A operand of the PV MMA); track the block max
 #pragma unroll 1
-        for (int c = 0; c < 128; c += 32) {
-          uint32_t v[32];
-          tmem_ld32(tS + c, v);
-          tmem_ld_wait();
-          uint32_t h[16];
+          for (int c = 0; c < 128; c += 32) {
+            uint32_t v[32];
+            tmem_ld32(tS + c, v);
+            tmem_ld_wait();
+            uint32_t h[16];
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sl2e, -mb));
-            float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sl2e, -mb));
-            if (ragged) {
-              if (kbase + c + i >= p.S) p0 = 0.f;
-              if (kbase + c + i + 1 >= p.S) p1 = 0.f;
+            for (int i = 0; i < 32; i += 2) {
+              float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
+              if (ragged) {
+                if (kbase + c + i >= p.S) s0 = -INFINITY;
+                if (kbase + c + i + 1 >= p.S) s1 = -INFINITY;
+              }
+              b0 = fmaxf(b0, s0);
+              b1 = fmaxf(b1, s1);
+              const float p0 = ex2_approx(fmaf(s0, sl2e, -mb));
+              const float p1 = ex2_approx(fmaf(s1, sl2e, -mb));
+              sum += p0 + p1;
+              __half2 t = __floats2half2_rn(p0, p1);
+              h[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
             }
-            sum += p0 + p1;
-            __half2 t = __floats2half2_rn(p0, p1);
-            h[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
-          }
-          uint8_t* panel = prow + (c >> 6) * (128 * 128);
-          const int ch0 = (c & 63) >> 3;  // first 16B chunk of this 32-key group inside the 128B row
+            uint8_t* panel = prow + (c >> 6) * (128 * 128);
+            const int ch0 = (c & 63) >> 3;  // first 16B chunk of this 32-key group inside the 128B row
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
-            *reinterpret_cast<uint4*>(panel + (((ch0 + u) ^ rx) << 4)) =
-                make_uint4(h[4 * u], h[4 * u + 1], h[4 * u + 2], h[4 * u + 3]);
-        }
+            for (int u = 0; u < 4; ++u)
+              *reinterpret_cast<uint4*>(panel + (((ch0 + u) ^ rx) << 4)) =
+                  make_uint4(h[4 * u], h[4 * u + 1], h[4 * u + 2], h[4 * u + 3]);
+          }
+          bmax = fmaxf(b0, b1);
+          // f16 P overflows beyond 2^16: redo the whole block (all lanes: the TMEM loads are warp-collective)
+          const bool over = (bmax - ref) * sl2e > 15.0f;
+          redo = __any_sync(0xffffffffu, over);
+          if (over) ref = bmax;
+        } while (redo);
         l = l * alpha + sum;
-        m = m_new;
+        m_prev = ref;
+        m = ((bmax - ref) * sl2e > 8.0f) ? bmax : ref;   // reference for the next block
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(&p_full[x]);

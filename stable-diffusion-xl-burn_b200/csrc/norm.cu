@@ -32,7 +32,19 @@ __global__ void gn_stats_kernel(const float* __restrict__ x1, int C1, const floa
   if (c < C1) { src = x1; cc = c; Cs = C1; } else { src = x2; cc = c - C1; Cs = C2; }
   src += (size_t)b * HW * Cs + cc;
   float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
-  for (int p = p0 + rr; p < p1; p += R) {
+  int p = p0 + rr;
+  for (; p + 3 * R < p1; p += 4 * R) {  // four independent 128-bit loads in flight per thread
+    float4 a[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a[u] = *reinterpret_cast<const float4*>(src + (size_t)(p + u * R) * Cs);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      s.x += a[u].x; s.y += a[u].y; s.z += a[u].z; s.w += a[u].w;
+      q.x = fmaf(a[u].x, a[u].x, q.x); q.y = fmaf(a[u].y, a[u].y, q.y);
+      q.z = fmaf(a[u].z, a[u].z, q.z); q.w = fmaf(a[u].w, a[u].w, q.w);
+    }
+  }
+  for (; p < p1; p += R) {
     const float4 a = *reinterpret_cast<const float4*>(src + (size_t)p * Cs);
     s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
     q.x = fmaf(a.x, a.x, q.x); q.y = fmaf(a.y, a.y, q.y); q.z = fmaf(a.z, a.z, q.z); q.w = fmaf(a.w, a.w, q.w);
@@ -103,15 +115,31 @@ __global__ void gn_apply_kernel(const float* __restrict__ x1, int C1, const floa
   __syncthreads();
   const int V8 = C >> 3;
   const long total = (long)HW * V8;
-  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long idx0 = (long)blockIdx.x * blockDim.x + threadIdx.x; idx0 < total; idx0 += 2 * stride) {
+    // two independent items per trip: both 32 B loads are issued before either is consumed
+    float4 la[2][2];
+    const float* srcs[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long idx = idx0 + u * stride;
+      if (idx < total) {
+        const int v = (int)(idx % V8);
+        const long p = idx / V8;
+        const int c = v * 8;
+        srcs[u] = (c < C1) ? x1 + ((size_t)b * HW + p) * C1 + c : x2 + ((size_t)b * HW + p) * C2 + (c - C1);
+        la[u][0] = *reinterpret_cast<const float4*>(srcs[u]);
+        la[u][1] = *reinterpret_cast<const float4*>(srcs[u] + 4);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+    const long idx = idx0 + u * stride;
+    if (idx >= total) continue;
     const int v = (int)(idx % V8);
     const long p = idx / V8;
     const int c = v * 8;
-    const float* src;
-    if (c < C1) src = x1 + ((size_t)b * HW + p) * C1 + c;
-    else src = x2 + ((size_t)b * HW + p) * C2 + (c - C1);
-    const float4 a0 = *reinterpret_cast<const float4*>(src);
-    const float4 a1 = *reinterpret_cast<const float4*>(src + 4);
+    const float4 a0 = la[u][0], a1 = la[u][1];
     float f[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
     uint32_t h[4];
     if (raw) {
@@ -134,6 +162,7 @@ __global__ void gn_apply_kernel(const float* __restrict__ x1, int C1, const floa
       h[i] = *reinterpret_cast<uint32_t*>(&t);
     }
     *reinterpret_cast<uint4*>(y + ((size_t)b * HW + p) * C + c) = make_uint4(h[0], h[1], h[2], h[3]);
+    }
   }
 }
 
