@@ -117,6 +117,22 @@ def test_qkv_attention(ctx, B, T, S, nh):
     assert torch.isfinite(out).all()
 
 
+@pytest.mark.parametrize("scale", [3.0, 6.0])
+def test_qkv_attention_large_dynamic_range(ctx, scale):
+    """Scores whose row maximum jumps by far more than 2^15 between key blocks: exercises the lazy-max overflow
+    fallback (the block is re-run with the exact maximum) and the rescale of the running sums."""
+    g = torch.Generator().manual_seed(int(scale * 10))
+    B, T, S, nh = 1, 256, 640, 2
+    q = h16(torch.randn(B, T, nh * 64, generator=g) * scale)
+    k = h16(torch.randn(B, S, nh * 64, generator=g) * scale)
+    k[:, 300:] *= 2.0  # later key blocks dominate
+    v = h16(torch.randn(B, S, nh * 64, generator=g))
+    ref = O.qkv_attention(q.float(), k.float(), v.float(), None, nh)
+    out = ctx.qkv_attention(q, k, v, None, nh)
+    assert torch.isfinite(out).all()
+    assert rel_err(out, ref) < 2e-3
+
+
 def test_qkv_attention_rejects_mask(ctx):
     from sdxl_b200 import SdxlError
     q = torch.zeros(1, 8, 64, dtype=torch.float16)
