@@ -713,12 +713,9 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_pair_kernel(const __grid_co
           tc_fence_after();
           {
             const uint32_t a_lo = a_lo0 + stage * stage_inc, b_lo = a_lo + b_off;
-            if (p.dbg_mode != 2) {
-#pragma unroll
-              for (int k = 0; k < kBlockK / 16; ++k)
-                tc_mma_f16_pair_elect(d_tmem, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            }
-            tc_commit_pair_elect(&empty_bar[stage]);  // frees the slot in both CTAs
+            // four MMAs + the commit that frees the slot in both CTAs, one elect
+            tc_mma4_commit_pair_elect(d_tmem, a_lo, b_lo, desc_hi, idesc, kb > 0 ? 1u : 0u, &empty_bar[stage],
+                                      p.dbg_mode != 2 ? 1u : 0u);
           }
           if (++stage == (uint32_t)nst) { stage = 0; phase ^= 1; }
         }

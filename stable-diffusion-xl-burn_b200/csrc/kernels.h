@@ -193,6 +193,18 @@ int axpby_launch(cudaStream_t st, float* x, const float* noise, size_t n, float 
 int randn_launch(cudaStream_t st, float* out, size_t n, uint64_t seed, uint64_t subseq);
 int dup_latent_f16_launch(cudaStream_t st, const float* x, size_t n, int nfwd, __half* x16);
 
+// Latent-decoder kernels (vae_kernels.cu)
+// P[r,:] = softmax(scale * S[r,:]); S f32 [rows, lds] -> P f16 [rows, ldp]; cols % 4 == 0.
+int softmax_rows_launch(cudaStream_t st, const float* S, size_t lds, int rows, int cols, float scale, __half* P,
+                        size_t ldp);
+// y[c, r] = x[r, c]; x f16 [rows, ldx], y f16 [cols, ldy].
+int transpose_f16_launch(cudaStream_t st, const __half* x, size_t ldx, int rows, int cols, __half* y, size_t ldy);
+// 1x1 conv on the rescaled latent: y = W (x * inv_scale) + b; NCHW f32 [B, C<=8, HW]; W f32 [C, C].
+int post_quant_launch(cudaStream_t st, const float* x, int B, int C, int HW, const float* w, const float* bias,
+                      float inv_scale, float* y);
+// u8[b,p,c] = trunc(clamp(((x+1)/2)*255, 0, 255)), c < 3, from NHWC f32 [npix, ldx].
+int image_u8_launch(cudaStream_t st, const float* x, long npix, int ldx, uint8_t* out);
+
 // Weight re-layout at load time (elementwise.cu)
 // Linear [K(in), N(out)] row-major f16 -> K-major [N, Kpad] f16 (zero padded), dst row pitch Kpad;
 // rows written at dst_row0 + perm(n) where perm handles the GEGLU value/gate interleave (geglu_bn>0).
