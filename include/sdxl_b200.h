@@ -189,6 +189,41 @@ SDXL_API int sdxl_op_layer_norm(sdxl_ctx* ctx, const float* x, const float* gamm
 SDXL_API int sdxl_op_timestep_embedding(sdxl_ctx* ctx, const int32_t* t_host, int n, int dim, int max_period,
                                float* out);
 
+/* ------------------------------------------------------------------------------------------------
+ * Latent decoder: replaces LatentDecoder::{decode_latent, latent_to_image}
+ * (reference src/model/stablediffusion/mod.rs:199-237, 263-266) over Autoencoder::decode_latent and Decoder::forward
+ * (src/model/autoencoder/mod.rs:66-69, 193-216). The reference hard-codes the layer widths
+ * (AutoencoderConfig::init, autoencoder/mod.rs:28-45); they are parameters here only so that tests can run a
+ * small instance. Weight names follow the reference's loader (autoencoder/load.rs): post_quant_conv,
+ * decoder/conv_in, decoder/mid/{block_1,attn,block_2}, decoder/blocks/<i>/{res1,res2,res3,upsampler},
+ * decoder/norm_out, decoder/conv_out; conv weights OIHW f16, biases / norm affine f16.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct sdxl_vae sdxl_vae;
+typedef struct sdxl_vae_cfg {
+  int32_t latent_channels;              /* 4 */
+  int32_t n_blocks;                     /* 4 */
+  int32_t block_in[SDXL_MAX_LEVELS];    /* 512, 512, 512, 256  (DecoderConfig channels, autoencoder/mod.rs:33) */
+  int32_t block_out[SDXL_MAX_LEVELS];   /* 512, 512, 256, 128 */
+  int32_t n_group;                      /* 32 */
+  double scale_factor;                  /* 0.13025 for SDXL (stablediffusion/load.rs:78) */
+} sdxl_vae_cfg;
+
+/* replaces load_latent_decoder (stablediffusion/load.rs:70-84): same flat pack container as sdxl_unet_load. */
+SDXL_API int sdxl_vae_load(sdxl_ctx* ctx, const sdxl_vae_cfg* cfg, const void* pack, size_t bytes, int pack_on_device,
+                           sdxl_vae** out);
+SDXL_API void sdxl_vae_destroy(sdxl_vae* vae);
+/* == LatentDecoder::decode_latent (stablediffusion/mod.rs:263-266): latent f32 [B,C,h,w] NCHW -> image f32
+ * [B,3,8h,8w] NCHW (nominally in [-1,1]). `on_host` != 0: both pointers are host memory. h*w must be a multiple of 64. */
+SDXL_API int sdxl_vae_decode_latent(sdxl_vae* vae, int B, int h, int w, const float* latent, int on_host, float* image_out);
+/* == LatentDecoder::latent_to_image (stablediffusion/mod.rs:200-237): RawImages buffer, u8 [B, 8h, 8w, 3],
+ * value = trunc(clamp(((x + 1) / 2) * 255, 0, 255)). */
+SDXL_API int sdxl_vae_latent_to_image(sdxl_vae* vae, int B, int h, int w, const float* latent, int on_host, uint8_t* rgb_out);
+/* algorithmic FLOPs (2*MAC over conv / linear / QK^T / PV) of the current decode plan; per-kind CUDA-event profile and
+ * per-op CSV as for the UNet plan. */
+SDXL_API double sdxl_vae_plan_flops(const sdxl_vae* vae);
+SDXL_API int sdxl_vae_profile_plan(sdxl_vae* vae, double* ms_by_kind, double* flops_by_kind, int* launches_by_kind);
+SDXL_API int sdxl_vae_profile_dump(sdxl_vae* vae, const char* path);
+
 #ifdef __cplusplus
 }
 #endif

@@ -286,12 +286,18 @@ struct Loader {
     return n;
   }
   // conv OIHW -> [O, ks*ks*Ipad (+ I2pad)]
-  Conv conv(const std::string& path, int I, int O, int ks, const std::string& skip_path = "", int I2 = 0) {
+  // Opad > O: the matrix (and bias) get zero rows up to Opad so the GEMM's N is a multiple of 4 (cv.O = Opad).
+  Conv conv(const std::string& path, int I, int O, int ks, const std::string& skip_path = "", int I2 = 0, int Opad = 0) {
     Conv cv;
     cv.I = I; cv.O = O; cv.ks = ks; cv.Ipad = pad64(I); cv.I2 = I2; cv.I2pad = I2 ? pad64(I2) : 0;
     cv.Ktot = ks * ks * cv.Ipad + cv.I2pad;
-    cv.w = A->get<__half>((size_t)O * cv.Ktot);
+    const int rows = Opad > O ? Opad : O;
+    cv.w = A->get<__half>((size_t)rows * cv.Ktot);
     if (!cv.w) { err = fail(c, 4005, "weight arena exhausted"); return cv; }
+    if (rows > O && !A->measure && cudaMemsetAsync(cv.w, 0, (size_t)rows * cv.Ktot * sizeof(__half), st) != cudaSuccess) {
+      err = fail(c, 4011, "memset failed");
+      return cv;
+    }
     const PackEntry* e = need(path + "/weight", 4);
     if (!e) return cv;
     if ((int)e->shape[0] != O || (int)e->shape[1] != I || (int)e->shape[2] != ks || (int)e->shape[3] != ks) {
@@ -301,7 +307,19 @@ struct Loader {
       return cv;
     }
     if (!A->measure) { int r = repack_conv_launch(st, ptr(e), O, I, ks, ks, cv.w, cv.Ktot, 0, cv.Ipad); if (r) err = fail(c, r, "repack_conv failed"); }
-    cv.b = vec_f32(path + "/bias", O);
+    if (rows > O) {
+      const PackEntry* be = need(path + "/bias", 1);
+      cv.b = A->get<float>(rows);
+      if (!be || !cv.b || (int)be->shape[0] != O) { if (!err) err = fail(c, 4012, "weight pack: '%s/bias' missing or mis-sized", path.c_str()); return cv; }
+      if (!A->measure) {
+        int r = (int)cudaMemsetAsync(cv.b, 0, rows * sizeof(float), st);
+        if (!r) r = bias_to_f32_launch(st, ptr(be), O, cv.b, 0, 0);
+        if (r) err = fail(c, r, "padded bias failed");
+      }
+      cv.O = rows;
+    } else {
+      cv.b = vec_f32(path + "/bias", O);
+    }
     if (I2) {
       const PackEntry* s = need(skip_path + "/weight", 4);
       if (!s) return cv;
@@ -610,7 +628,10 @@ extern "C" int sdxl_unet_load(sdxl_ctx* c, const sdxl_unet_cfg* cfg, const void*
 // ================================================================================================
 // launch plan
 // ================================================================================================
-enum OpKind { OP_IGEMM, OP_ATTN, OP_GN, OP_LN, OP_GEMV, OP_TEMB, OP_CONV_IN, OP_UPS, OP_PHASE, OP_CAST16 };
+enum OpKind { OP_IGEMM, OP_ATTN, OP_GN, OP_LN, OP_GEMV, OP_TEMB, OP_CONV_IN, OP_UPS, OP_PHASE, OP_CAST16,
+              OP_SOFTMAX, OP_TRANSPOSE, OP_PQ };
+static const char* const kOpNames[] = {"igemm", "attention", "group_norm", "layer_norm", "gemv", "temb", "conv_in", "upsample",
+                                       "phase_split", "cast16", "softmax_rows", "transpose16", "post_quant"};
 struct Op {
   OpKind kind;
   double flops = 0;  // algorithmic FLOPs of this launch (igemm / attention), 0 for HBM-bound ops
@@ -623,6 +644,9 @@ struct Op {
   struct { const float* x; int Bx, B, Cin, H, W; const float* w; const float* bias; int Cout; float* y; } ci;
   struct { const float* x; int B, H, W, C; __half* y; } rs;  // upsample / phase split
   struct { const float* x; size_t n; __half* y; } cs;
+  struct { const float* S; size_t lds; int rows, cols; float scale; __half* P; size_t ldp; } sm;
+  struct { const __half* x; size_t ldx; int rows, cols; __half* y; size_t ldy; } tr;
+  struct { const float* x; int B, C, HW; const float* w; const float* bias; float inv_scale; float* y; } pq;
 };
 
 struct Plan {
@@ -830,6 +854,9 @@ static int exec_op(sdxl_ctx* c, Op& op) {
     case OP_UPS: KL(c, upsample2x_launch(st, op.rs.x, op.rs.B, op.rs.H, op.rs.W, op.rs.C, op.rs.y)); break;
     case OP_PHASE: KL(c, phase_split_launch(st, op.rs.x, op.rs.B, op.rs.H, op.rs.W, op.rs.C, op.rs.y)); break;
     case OP_CAST16: KL(c, cast_f32_to_f16_launch(st, op.cs.x, op.cs.n, op.cs.y)); break;
+    case OP_SOFTMAX: KL(c, softmax_rows_launch(st, op.sm.S, op.sm.lds, op.sm.rows, op.sm.cols, op.sm.scale, op.sm.P, op.sm.ldp)); break;
+    case OP_TRANSPOSE: KL(c, transpose_f16_launch(st, op.tr.x, op.tr.ldx, op.tr.rows, op.tr.cols, op.tr.y, op.tr.ldy)); break;
+    case OP_PQ: KL(c, post_quant_launch(st, op.pq.x, op.pq.B, op.pq.C, op.pq.HW, op.pq.w, op.pq.bias, op.pq.inv_scale, op.pq.y)); break;
   }
   return 0;
 }
@@ -1005,9 +1032,7 @@ static int ensure_plan(sdxl_unet* u, int Bf, int Bx, int h, int w) {
   return 0;
 }
 
-static int run_plan(sdxl_unet* u) {
-  sdxl_ctx* c = u->ctx;
-  Plan* P = u->plan.get();
+static int run_plan_ops(sdxl_ctx* c, Plan* P) {
   static const bool no_graph = getenv("SDXL_B200_NO_GRAPH") != nullptr;
   if (P->gexec) {
     CU(c, cudaGraphLaunch(P->gexec, c->stream));
@@ -1034,6 +1059,7 @@ static int run_plan(sdxl_unet* u) {
   P->runs++;
   return r;
 }
+static int run_plan(sdxl_unet* u) { return run_plan_ops(u->ctx, u->plan.get()); }
 
 static int set_t(sdxl_unet* u, int t) {
   sdxl_ctx* c = u->ctx;
@@ -1155,10 +1181,7 @@ extern "C" int sdxl_unet_forward_f32(sdxl_unet* u, int B, int h, int w, const fl
 }
 // Per-kernel-kind device time of one plan execution, measured with CUDA events on the ctx stream
 // (eager launches, one event pair per op). kinds: see OpKind. Arrays must hold 16 entries.
-extern "C" int sdxl_unet_profile_plan(sdxl_unet* u, double* ms_by_kind, double* flops_by_kind, int* launches_by_kind) {
-  if (!u || !u->plan) return -1;
-  sdxl_ctx* c = u->ctx;
-  Plan* P = u->plan.get();
+static int profile_plan_impl(sdxl_ctx* c, Plan* P, double* ms_by_kind, double* flops_by_kind, int* launches_by_kind) {
   const size_t n = P->ops.size();
   std::vector<cudaEvent_t> ev(n + 1);
   for (auto& e : ev) CU(c, cudaEventCreate(&e));
@@ -1183,11 +1206,12 @@ extern "C" int sdxl_unet_profile_plan(sdxl_unet* u, double* ms_by_kind, double* 
   if (se != cudaSuccess) return fail(c, (int)se, "profile run failed: %s", cudaGetErrorString(se));
   return r;
 }
+extern "C" int sdxl_unet_profile_plan(sdxl_unet* u, double* ms_by_kind, double* flops_by_kind, int* launches_by_kind) {
+  if (!u || !u->plan) return -1;
+  return profile_plan_impl(u->ctx, u->plan.get(), ms_by_kind, flops_by_kind, launches_by_kind);
+}
 // Per-op dump of one eager plan execution (CUDA-event time per launch) as CSV: analysis aid for profiles/.
-extern "C" int sdxl_unet_profile_dump(sdxl_unet* u, const char* path) {
-  if (!u || !u->plan || !path) return -1;
-  sdxl_ctx* c = u->ctx;
-  Plan* P = u->plan.get();
+static int profile_dump_impl(sdxl_ctx* c, Plan* P, const char* path) {
   const size_t n = P->ops.size();
   std::vector<cudaEvent_t> ev(n + 1);
   for (auto& e : ev) CU(c, cudaEventCreate(&e));
@@ -1203,7 +1227,6 @@ extern "C" int sdxl_unet_profile_dump(sdxl_unet* u, const char* path) {
     if (!f) r = fail(c, -3, "cannot open %s", path);
     else {
       fprintf(f, "op,kind,us,gflop,tflops,M_tiles,N,BN,Kblocks,T,S,heads,cluster\n");
-      static const char* names[] = {"igemm", "attention", "group_norm", "layer_norm", "gemv", "temb", "conv_in", "upsample", "phase_split", "cast16"};
       for (size_t i = 0; i < n; ++i) {
         float ms = 0;
         cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
@@ -1213,7 +1236,7 @@ extern "C" int sdxl_unet_profile_dump(sdxl_unet* u, const char* path) {
           mt = o.ig.tilesW * o.ig.tilesH * o.ig.tilesB; N = o.ig.N; BN = o.ig.BN;
           for (int s2 = 0; s2 < o.ig.nseg; ++s2) kb += o.ig.seg[s2].nkb;
         } else if (o.kind == OP_ATTN) { T = o.at.T; S = o.at.S; H = o.at.n_head; }
-        fprintf(f, "%zu,%s,%.2f,%.3f,%.1f,%d,%d,%d,%d,%d,%d,%d,%dx%d\n", i, names[o.kind], ms * 1e3, o.flops * 1e-9,
+        fprintf(f, "%zu,%s,%.2f,%.3f,%.1f,%d,%d,%d,%d,%d,%d,%d,%dx%d\n", i, kOpNames[o.kind], ms * 1e3, o.flops * 1e-9,
                 ms > 0 ? o.flops / (ms * 1e-3) * 1e-12 : 0.0, mt, N, BN, kb, T, S, H,
                 o.kind == OP_IGEMM ? (o.ig.pair ? 9 : o.ig.CM) : 0, o.kind == OP_IGEMM ? o.ig.CN : 0);
       }
@@ -1223,6 +1246,10 @@ extern "C" int sdxl_unet_profile_dump(sdxl_unet* u, const char* path) {
   for (auto& e : ev) cudaEventDestroy(e);
   if (se != cudaSuccess) return fail(c, (int)se, "profile run failed: %s", cudaGetErrorString(se));
   return r;
+}
+extern "C" int sdxl_unet_profile_dump(sdxl_unet* u, const char* path) {
+  if (!u || !u->plan || !path) return -1;
+  return profile_dump_impl(u->ctx, u->plan.get(), path);
 }
 extern "C" double sdxl_unet_alpha(const sdxl_unet* u, int i) {
   if (!u || i < 0 || i >= (int)u->alphas.size()) return NAN;
@@ -1619,4 +1646,404 @@ extern "C" int sdxl_dbg_igemm_timeline(sdxl_ctx* c, int M, int K, int N, int geg
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   return 0;
+}
+
+// ================================================================================================
+// Latent decoder: LatentDecoder::{decode_latent, latent_to_image}
+//   Autoencoder::decode_latent      src/model/autoencoder/mod.rs:66-69
+//   Decoder::forward                src/model/autoencoder/mod.rs:202-216
+//   Mid / ResnetBlock / ConvSelfAttentionBlock / DecoderBlock
+//                                   src/model/autoencoder/mod.rs:436-452, 507-524, 548-586, 298-324
+//   LatentDecoder                   src/model/stablediffusion/mod.rs:199-237, 263-266
+// Same machinery as the UNet: weights re-laid-out once on the device, a flat launch plan replayed as a CUDA graph.
+// All convolutions and the attention contractions run on the tcgen05 implicit-GEMM kernel with f16 operands and f32
+// accumulation; the residual stream, GroupNorm statistics, the score matrix and the softmax are f32 (the reference
+// runs this module in f32 end to end; tests/test_vae_gpu.py states the resulting tolerance).
+// The attention block is single-head with d = C (512): scores are materialised (f32 [T,T] per image, 1.07 GB at
+// 1024^2), soft-maxed by rows into f16 probabilities and multiplied with V by a second GEMM.
+// ================================================================================================
+struct VRes {
+  Norm n1, n2;
+  Conv c1, c2;  // c2 carries the fused nin_shortcut 1x1 segment when Cin != Cout
+  int Cin = 0, Cout = 0;
+  bool has_skip = false;
+};
+struct VBlock {
+  VRes r[3];
+  bool up = false;
+  Conv upc;
+  int Cout = 0;
+};
+struct sdxl_vae {
+  sdxl_ctx* ctx = nullptr;
+  sdxl_vae_cfg cfg{};
+  Arena warena;
+  float* pq_w = nullptr;   // [Cl, Cl] f32
+  float* pq_b = nullptr;
+  float* cin_w = nullptr;  // [C0][3][3][Cl] f32
+  float* cin_b = nullptr;
+  int C0 = 0;
+  VRes mid1, mid2;
+  Norm attn_norm;
+  Lin aq, ak, av, aproj;
+  std::vector<VBlock> blocks;
+  Norm norm_out;
+  Conv conv_out;  // O padded to 4
+  std::unique_ptr<Plan> plan;
+  float* img_nhwc = nullptr;     // [B, 64hw, 4] f32 (decoder output, first 3 channels valid)
+  float* out_f32 = nullptr;      // [B, 3, 8h, 8w] staging for host reads
+  uint8_t* out_u8 = nullptr;     // [B, 8h, 8w, 3]
+};
+
+static Lin lin_from_conv1x1(const Conv& cv) {
+  Lin L;
+  L.w = cv.w; L.b = cv.b; L.K = cv.I; L.Kpad = cv.Ipad; L.N = cv.O;
+  return L;
+}
+static VRes load_vres(Loader& L, const std::string& path, int Cin, int Cout) {
+  VRes r;
+  r.Cin = Cin; r.Cout = Cout; r.has_skip = (Cin != Cout);
+  r.n1 = L.norm(path + "/norm1", Cin);
+  r.c1 = L.conv(path + "/conv1", Cin, Cout, 3);
+  r.n2 = L.norm(path + "/norm2", Cout);
+  if (r.has_skip) r.c2 = L.conv(path + "/conv2", Cout, Cout, 3, path + "/nin_shortcut", Cin);
+  else r.c2 = L.conv(path + "/conv2", Cout, Cout, 3);
+  return r;
+}
+static int build_vae(sdxl_vae* v, const PackView& pv, Arena& A) {
+  sdxl_ctx* c = v->ctx;
+  const sdxl_vae_cfg& g = v->cfg;
+  Loader L{nullptr, c, &pv, &A, c->stream};
+  const int Cl = g.latent_channels;
+  v->blocks.clear();
+  v->C0 = g.block_in[0];
+  // post_quant_conv: OIHW [Cl,Cl,1,1] f16 -> f32 [Cl][Cl]
+  {
+    const PackEntry* e = L.need("post_quant_conv/weight", 4);
+    if (!e) return L.err;
+    if ((int)e->shape[0] != Cl || (int)e->shape[1] != Cl || e->shape[2] != 1 || e->shape[3] != 1) return fail(c, 4301, "post_quant_conv/weight bad shape");
+    v->pq_w = A.get<float>((size_t)Cl * Cl);
+    if (!v->pq_w) return fail(c, 4005, "weight arena exhausted");
+    if (!A.measure) { int r = cast_f16_to_f32_launch(c->stream, L.ptr(e), (size_t)Cl * Cl, v->pq_w); if (r) return fail(c, r, "post_quant cast failed"); }
+    v->pq_b = L.vec_f32("post_quant_conv/bias", Cl);
+    if (L.err) return L.err;
+  }
+  // decoder/conv_in: OIHW f16 -> [O][kh][kw][I] f32 (CUDA-core kernel, exact f32 like the reference)
+  {
+    const PackEntry* e = L.need("decoder/conv_in/weight", 4);
+    if (!e) return L.err;
+    if ((int)e->shape[0] != v->C0 || (int)e->shape[1] != Cl || e->shape[2] != 3 || e->shape[3] != 3) return fail(c, 4302, "decoder/conv_in/weight bad shape");
+    const size_t n = (size_t)v->C0 * 9 * Cl;
+    __half* tmp = A.get<__half>(n);
+    v->cin_w = A.get<float>(n);
+    if (!tmp || !v->cin_w) return fail(c, 4005, "weight arena exhausted");
+    if (!A.measure) {
+      int r = repack_conv_launch(c->stream, L.ptr(e), v->C0, Cl, 3, 3, tmp, 9 * Cl, 0, Cl);
+      if (!r) r = cast_f16_to_f32_launch(c->stream, tmp, n, v->cin_w);
+      if (r) return fail(c, r, "decoder conv_in repack failed");
+    }
+    v->cin_b = L.vec_f32("decoder/conv_in/bias", v->C0);
+    if (L.err) return L.err;
+  }
+  const int Cm = v->C0;
+  v->mid1 = load_vres(L, "decoder/mid/block_1", Cm, Cm);
+  v->attn_norm = L.norm("decoder/mid/attn/norm", Cm);
+  v->aq = lin_from_conv1x1(L.conv("decoder/mid/attn/q", Cm, Cm, 1));
+  v->ak = lin_from_conv1x1(L.conv("decoder/mid/attn/k", Cm, Cm, 1));
+  v->av = lin_from_conv1x1(L.conv("decoder/mid/attn/v", Cm, Cm, 1));
+  v->aproj = lin_from_conv1x1(L.conv("decoder/mid/attn/proj_out", Cm, Cm, 1));
+  v->mid2 = load_vres(L, "decoder/mid/block_2", Cm, Cm);
+  if (L.err) return L.err;
+  for (int i = 0; i < g.n_blocks && !L.err; ++i) {
+    VBlock b;
+    const std::string bp = "decoder/blocks/" + std::to_string(i);
+    const int ci = g.block_in[i], co = g.block_out[i];
+    b.Cout = co;
+    b.r[0] = load_vres(L, bp + "/res1", ci, co);
+    b.r[1] = load_vres(L, bp + "/res2", co, co);
+    b.r[2] = load_vres(L, bp + "/res3", co, co);
+    b.up = (i != g.n_blocks - 1);
+    if (b.up) b.upc = L.conv(bp + "/upsampler", co, co, 3);
+    v->blocks.push_back(b);
+  }
+  if (L.err) return L.err;
+  const int Cf = g.block_out[g.n_blocks - 1];
+  v->norm_out = L.norm("decoder/norm_out", Cf);
+  v->conv_out = L.conv("decoder/conv_out", Cf, 3, 3, "", 0, 4);
+  return L.err;
+}
+
+extern "C" void sdxl_vae_destroy(sdxl_vae* v) {
+  if (!v) return;
+  cudaStreamSynchronize(v->ctx->stream);
+  v->plan.reset();
+  v->warena.release();
+  delete v;
+}
+
+extern "C" int sdxl_vae_load(sdxl_ctx* c, const sdxl_vae_cfg* cfg, const void* pack, size_t bytes, int pack_on_device,
+                             sdxl_vae** out) {
+  if (!c || !cfg || !pack || !out) return fail(c, -1, "sdxl_vae_load: null argument");
+  *out = nullptr;
+  if (cfg->n_blocks < 1 || cfg->n_blocks > SDXL_MAX_LEVELS) return fail(c, 4310, "bad n_blocks");
+  if (cfg->latent_channels < 1 || cfg->latent_channels > 8) return fail(c, 4311, "latent_channels must be 1..8");
+  if (cfg->n_group != 32) return fail(c, 4312, "n_group must be 32 (got %d)", cfg->n_group);
+  if (!(cfg->scale_factor > 0)) return fail(c, 4313, "scale_factor must be positive");
+  for (int i = 0; i < cfg->n_blocks; ++i) {
+    if (cfg->block_in[i] % 64 || cfg->block_out[i] % 64) return fail(c, 4314, "decoder widths must be multiples of 64");
+    if (i && cfg->block_in[i] != cfg->block_out[i - 1]) return fail(c, 4315, "block_in[%d] != block_out[%d]", i, i - 1);
+  }
+  CU(c, cudaSetDevice(c->device));
+  std::unique_ptr<sdxl_vae> v(new sdxl_vae());
+  v->ctx = c;
+  v->cfg = *cfg;
+  PackView pv;
+  std::vector<uint8_t> table;
+  int r = parse_pack(c, pack, bytes, pack_on_device, pv, table);
+  if (r) return r;
+  void* dev_pack = nullptr;
+  if (pack_on_device) {
+    pv.dev = (const uint8_t*)pack;
+  } else {
+    CU(c, cudaMalloc(&dev_pack, bytes));
+    cudaError_t e = cudaMemcpyAsync(dev_pack, pack, bytes, cudaMemcpyHostToDevice, c->stream);
+    if (e != cudaSuccess) { cudaFree(dev_pack); return fail(c, (int)e, "pack upload failed"); }
+    pv.dev = (const uint8_t*)dev_pack;
+  }
+  Arena meas;
+  meas.measure = true;
+  r = build_vae(v.get(), pv, meas);
+  if (!r && v->warena.init(meas.off + (1 << 20))) r = fail(c, 4203, "cannot allocate %zu bytes for weights", meas.off);
+  if (!r) r = build_vae(v.get(), pv, v->warena);
+  cudaError_t se = cudaStreamSynchronize(c->stream);
+  if (dev_pack) cudaFree(dev_pack);
+  if (!r && se != cudaSuccess) r = fail(c, (int)se, "weight re-layout failed: %s", cudaGetErrorString(se));
+  if (r) { v->warena.release(); return r; }
+  *out = v.release();
+  return 0;
+}
+
+// Builds the op list of Decoder::forward at batch B, latent h x w.
+static int build_vae_plan(sdxl_vae* v, Plan* P, Arena* A) {
+  sdxl_ctx* c = v->ctx;
+  const sdxl_vae_cfg& g = v->cfg;
+  PlanBuilder B{nullptr, c, P, A, P->Bf};
+  P->ops.clear();
+  P->flops = 0;
+  const int Bn = P->Bf, Cl = g.latent_channels;
+  int H = P->h, W = P->w;
+  if ((H * W) % 64) return fail(c, 5101, "latent %dx%d: h*w must be a multiple of 64", H, W);
+
+  // buffer maxima over the stages
+  size_t max_x = (size_t)H * W * v->C0, max_in = max_x, max_out = max_x, max_up = 0;
+  {
+    int hh = H, ww = W;
+    for (const VBlock& b : v->blocks) {
+      for (int k = 0; k < 3; ++k) {
+        max_in = std::max(max_in, (size_t)hh * ww * b.r[k].Cin);
+        max_out = std::max(max_out, (size_t)hh * ww * b.r[k].Cout);
+      }
+      if (b.up) { hh *= 2; ww *= 2; max_up = std::max(max_up, (size_t)hh * ww * b.Cout); }
+      max_x = std::max(max_x, (size_t)hh * ww * b.Cout);
+    }
+    max_in = std::max(max_in, max_x);  // norm_out operand
+  }
+  P->x_in = B.buf<float>((size_t)Bn * Cl * H * W);
+  float* pq_out = B.buf<float>((size_t)Bn * Cl * H * W);
+  B.gn_partial = B.buf<float>(gn_scratch_floats(Bn, 32));
+  float* xb[2] = {B.buf<float>(Bn * max_x), B.buf<float>(Bn * max_x)};
+  __half* s_gn1 = B.buf<__half>(Bn * max_in);
+  __half* s_raw = B.buf<__half>(Bn * max_in);
+  float* s_h = B.buf<float>(Bn * max_out);
+  __half* s_gn2 = B.buf<__half>(Bn * max_out);
+  __half* s_up = max_up ? B.buf<__half>(Bn * max_up) : nullptr;
+  const int T = H * W, Cm = v->C0;
+  __half* q16 = B.buf<__half>((size_t)Bn * T * Cm);
+  __half* k16 = B.buf<__half>((size_t)Bn * T * Cm);
+  __half* v16 = B.buf<__half>((size_t)Bn * T * Cm);
+  __half* vT = B.buf<__half>((size_t)T * Cm);
+  __half* ao = B.buf<__half>((size_t)Bn * T * Cm);
+  float* S = B.buf<float>((size_t)T * T);
+  __half* Pm = B.buf<__half>((size_t)T * T);
+  if (B.err) return B.err;
+
+  int cur = 0;
+  auto vres = [&](const VRes& r) {
+    const int HW = H * W;
+    float* x = xb[cur];
+    float* out = xb[cur ^ 1];
+    B.gn(x, r.Cin, nullptr, 0, HW, r.n1, 1, s_gn1, r.has_skip ? s_raw : nullptr);
+    ActView a1{s_gn1, Bn, H, W, r.Cin};
+    B.conv3(a1, nullptr, r.c1, s_h, r.c1.b, 0, nullptr);
+    B.gn(s_h, r.Cout, nullptr, 0, HW, r.n2, 1, s_gn2, nullptr);
+    ActView a2{s_gn2, Bn, H, W, r.Cout};
+    if (r.has_skip) {
+      ActView sk{s_raw, Bn, H, W, r.Cin};
+      B.conv3(a2, &sk, r.c2, out, r.c2.b, 0, nullptr);  // nin_shortcut(x) + h as one GEMM (autoencoder/mod.rs:519-523)
+    } else {
+      B.conv3(a2, nullptr, r.c2, out, r.c2.b, 0, x);
+    }
+    cur ^= 1;
+  };
+
+  // post_quant_conv(latent / scale_factor), conv_in
+  {
+    Op op{};
+    op.kind = OP_PQ;
+    op.pq = {P->x_in, Bn, Cl, H * W, v->pq_w, v->pq_b, (float)(1.0 / g.scale_factor), pq_out};
+    P->ops.push_back(op);
+    P->flops += 2.0 * Bn * H * W * (double)Cl * Cl;
+  }
+  {
+    Op op{};
+    op.kind = OP_CONV_IN;
+    op.ci = {pq_out, Bn, Bn, Cl, H, W, v->cin_w, v->cin_b, v->C0, xb[cur]};
+    P->ops.push_back(op);
+    P->flops += 2.0 * Bn * H * W * 9.0 * Cl * v->C0;
+  }
+  // mid: ResnetBlock, ConvSelfAttentionBlock, ResnetBlock
+  vres(v->mid1);
+  {
+    float* x = xb[cur];
+    float* out = xb[cur ^ 1];
+    const int M = Bn * T;
+    B.gn(x, Cm, nullptr, 0, T, v->attn_norm, 0, s_gn1, nullptr);
+    B.linear(s_gn1, M, v->aq, IGEMM_LINEAR, q16, 0, Cm, nullptr, 0);
+    B.linear(s_gn1, M, v->ak, IGEMM_LINEAR, k16, 0, Cm, nullptr, 0);
+    B.linear(s_gn1, M, v->av, IGEMM_LINEAR, v16, 0, Cm, nullptr, 0);
+    const int Kp = Loader::pad64(Cm);
+    for (int b = 0; b < Bn && !B.err; ++b) {
+      const size_t o = (size_t)b * T * Cm;
+      {  // S = q k^T  (f32)
+        ActView a{q16 + o, 1, 1, T, Cm};
+        std::vector<IgemmSeg> segs{{0, 0, 0, 0, Kp / 64}};
+        B.igemm(a, nullptr, segs, k16 + o, T, Kp, 1, T, 1, IGEMM_LINEAR, 0, S, 1, T, nullptr, 0, nullptr, 0);
+        B.add_flops(2.0 * T * (double)T * Cm);
+      }
+      {
+        Op op{};
+        op.kind = OP_SOFTMAX;
+        op.sm = {S, (size_t)T, T, T, (float)(1.0 / sqrt((double)Cm)), Pm, (size_t)T};
+        P->ops.push_back(op);
+      }
+      {
+        Op op{};
+        op.kind = OP_TRANSPOSE;
+        op.tr = {v16 + o, (size_t)Cm, T, Cm, vT, (size_t)T};
+        P->ops.push_back(op);
+      }
+      {  // O = P v
+        ActView a{Pm, 1, 1, T, T};
+        std::vector<IgemmSeg> segs{{0, 0, 0, 0, T / 64}};
+        B.igemm(a, nullptr, segs, vT, Cm, T, 1, T, 1, IGEMM_LINEAR, 0, ao + o, 0, Cm, nullptr, 0, nullptr, 0);
+        B.add_flops(2.0 * T * (double)T * Cm);
+      }
+    }
+    B.linear(ao, M, v->aproj, IGEMM_LINEAR, out, 1, Cm, x, Cm);  // x + proj_out(attn)
+    cur ^= 1;
+  }
+  vres(v->mid2);
+  // up blocks
+  for (const VBlock& b : v->blocks) {
+    if (B.err) break;
+    for (int k = 0; k < 3; ++k) vres(b.r[k]);
+    if (b.up) {
+      // nearest-2x then 3x3 conv (autoencoder/mod.rs:311-319)
+      Op op{};
+      op.kind = OP_UPS;
+      op.rs = {xb[cur], Bn, H, W, b.Cout, s_up};
+      P->ops.push_back(op);
+      H *= 2; W *= 2;
+      ActView a{s_up, Bn, H, W, b.Cout};
+      B.conv3(a, nullptr, b.upc, xb[cur ^ 1], b.upc.b, 0, nullptr);
+      cur ^= 1;
+    }
+  }
+  if (B.err) return B.err;
+  // head: GN -> SiLU -> conv 3x3 to RGB (autoencoder/mod.rs:213-214); N padded to 4
+  const int Cf = g.block_out[g.n_blocks - 1];
+  B.gn(xb[cur], Cf, nullptr, 0, H * W, v->norm_out, 1, s_gn1, nullptr);
+  v->img_nhwc = B.buf<float>((size_t)Bn * H * W * 4);
+  {
+    ActView a{s_gn1, Bn, H, W, Cf};
+    std::vector<IgemmSeg> segs;
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw) segs.push_back({0, (int16_t)(kw - 1), (int16_t)(kh - 1), 0, v->conv_out.Ipad / 64});
+    B.igemm(a, nullptr, segs, v->conv_out.w, 4, v->conv_out.Ktot, H, W, Bn, IGEMM_LINEAR, 0, v->img_nhwc, 1, 4, v->conv_out.b, 0,
+            nullptr, 0);
+    B.add_flops(2.0 * Bn * H * W * 9.0 * Cf * 3);
+  }
+  v->out_f32 = B.buf<float>((size_t)Bn * 3 * H * W);
+  v->out_u8 = B.buf<uint8_t>((size_t)Bn * 3 * H * W);
+  return B.err;
+}
+
+static int vae_ensure_plan(sdxl_vae* v, int Bn, int h, int w) {
+  sdxl_ctx* c = v->ctx;
+  if (Bn < 1 || h < 1 || w < 1) return fail(c, 5100, "bad decode shape B=%d h=%d w=%d", Bn, h, w);
+  if (v->plan && v->plan->Bf == Bn && v->plan->h == h && v->plan->w == w) return 0;
+  CU(c, cudaStreamSynchronize(c->stream));
+  v->plan.reset(new Plan());
+  Plan* P = v->plan.get();
+  P->Bf = Bn; P->Bx = Bn; P->h = h; P->w = w;
+  Arena meas;
+  meas.measure = true;
+  int r = build_vae_plan(v, P, &meas);
+  if (r) { v->plan.reset(); return r; }
+  if (P->arena.init(meas.off + (1 << 20))) { v->plan.reset(); return fail(c, 5011, "cannot allocate %zu bytes of workspace", meas.off); }
+  r = build_vae_plan(v, P, &P->arena);
+  if (r) { v->plan.reset(); return r; }
+  return 0;
+}
+
+static int vae_run(sdxl_vae* v, int Bn, int h, int w, const float* latent, int on_host) {
+  sdxl_ctx* c = v->ctx;
+  if (!latent) return fail(c, -1, "null latent");
+  CU(c, cudaSetDevice(c->device));
+  int r = vae_ensure_plan(v, Bn, h, w);
+  if (r) return r;
+  Plan* P = v->plan.get();
+  const size_t n = (size_t)Bn * v->cfg.latent_channels * h * w;
+  CU(c, cudaMemcpyAsync(P->x_in, latent, n * sizeof(float), on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, c->stream));
+  return run_plan_ops(c, P);
+}
+
+extern "C" int sdxl_vae_decode_latent(sdxl_vae* v, int Bn, int h, int w, const float* latent, int on_host, float* image_out) {
+  if (!v || !image_out) return fail(v ? v->ctx : nullptr, -1, "sdxl_vae_decode_latent: null argument");
+  sdxl_ctx* c = v->ctx;
+  int r = vae_run(v, Bn, h, w, latent, on_host);
+  if (r) return r;
+  const int up = 1 << (v->cfg.n_blocks - 1);
+  const int HW = h * up * w * up;
+  float* dst = on_host ? v->out_f32 : image_out;
+  KL(c, nhwc_to_nchw_f32_launch(c->stream, v->img_nhwc, Bn, HW, 3, 4, dst));
+  if (on_host) {
+    CU(c, cudaMemcpyAsync(image_out, dst, (size_t)Bn * 3 * HW * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+  }
+  return 0;
+}
+extern "C" int sdxl_vae_latent_to_image(sdxl_vae* v, int Bn, int h, int w, const float* latent, int on_host, uint8_t* rgb_out) {
+  if (!v || !rgb_out) return fail(v ? v->ctx : nullptr, -1, "sdxl_vae_latent_to_image: null argument");
+  sdxl_ctx* c = v->ctx;
+  int r = vae_run(v, Bn, h, w, latent, on_host);
+  if (r) return r;
+  const int up = 1 << (v->cfg.n_blocks - 1);
+  const long npix = (long)Bn * h * up * w * up;
+  uint8_t* dst = on_host ? v->out_u8 : rgb_out;
+  KL(c, image_u8_launch(c->stream, v->img_nhwc, npix, 4, dst));
+  if (on_host) {
+    CU(c, cudaMemcpyAsync(rgb_out, dst, (size_t)npix * 3, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+  }
+  return 0;
+}
+extern "C" double sdxl_vae_plan_flops(const sdxl_vae* v) { return (v && v->plan) ? v->plan->flops : 0.0; }
+extern "C" int sdxl_vae_profile_plan(sdxl_vae* v, double* ms_by_kind, double* flops_by_kind, int* launches_by_kind) {
+  if (!v || !v->plan) return -1;
+  return profile_plan_impl(v->ctx, v->plan.get(), ms_by_kind, flops_by_kind, launches_by_kind);
+}
+extern "C" int sdxl_vae_profile_dump(sdxl_vae* v, const char* path) {
+  if (!v || !v->plan || !path) return -1;
+  return profile_dump_impl(v->ctx, v->plan.get(), path);
 }

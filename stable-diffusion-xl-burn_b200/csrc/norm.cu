@@ -33,12 +33,12 @@ __global__ void gn_stats_kernel(const float* __restrict__ x1, int C1, const floa
   src += (size_t)b * HW * Cs + cc;
   float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
   int p = p0 + rr;
-  for (; p + 3 * R < p1; p += 4 * R) {  // four independent 128-bit loads in flight per thread
-    float4 a[4];
+  for (; p + 7 * R < p1; p += 8 * R) {  // eight independent 128-bit loads in flight per thread
+    float4 a[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) a[u] = *reinterpret_cast<const float4*>(src + (size_t)(p + u * R) * Cs);
+    for (int u = 0; u < 8; ++u) a[u] = *reinterpret_cast<const float4*>(src + (size_t)(p + u * R) * Cs);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       s.x += a[u].x; s.y += a[u].y; s.z += a[u].z; s.w += a[u].w;
       q.x = fmaf(a[u].x, a[u].x, q.x); q.y = fmaf(a[u].y, a[u].y, q.y);
       q.z = fmaf(a[u].z, a[u].z, q.z); q.w = fmaf(a[u].w, a[u].w, q.w);
@@ -171,9 +171,9 @@ int gn_launch(cudaStream_t st, GnParams& p) {
   if ((p.C1 & 7) || (p.C2 & 7) || C % p.n_group || p.n_group > 64) return 3001;
   const int V = C / 4;
   if (V > 1024) return 3002;
-  int R = 384 / V;
+  int R = 512 / V;
   if (R < 1) R = 1;
-  if (R > 8) R = 8;
+  if (R > 16) R = 16;
   // chunking depends on HW only (never on the batch size): every sample's statistics are summed in the
   // same order whatever B is, which keeps the whole forward batch-invariant bit for bit.
   int nchunk = 148;

@@ -42,6 +42,14 @@ class Conditioning(C.Structure):
     ]
 
 
+class VaeCfg(C.Structure):
+    _fields_ = [
+        ("latent_channels", C.c_int32), ("n_blocks", C.c_int32),
+        ("block_in", C.c_int32 * SDXL_MAX_LEVELS), ("block_out", C.c_int32 * SDXL_MAX_LEVELS),
+        ("n_group", C.c_int32), ("scale_factor", C.c_double),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/sdxl_b200.h declares
 P = C.c_void_p
 I = C.c_int
@@ -75,6 +83,13 @@ PROTOTYPES = {
     "sdxl_op_group_norm": (I, [P, P, I, P, I, I, I, I, P, P, C.c_float, I, P]),
     "sdxl_op_layer_norm": (I, [P, P, P, P, C.c_float, I, I, P]),
     "sdxl_op_timestep_embedding": (I, [P, P, I, I, I, P]),
+    "sdxl_vae_load": (I, [P, C.POINTER(VaeCfg), P, C.c_size_t, I, C.POINTER(P)]),
+    "sdxl_vae_destroy": (None, [P]),
+    "sdxl_vae_decode_latent": (I, [P, I, I, I, P, I, P]),
+    "sdxl_vae_latent_to_image": (I, [P, I, I, I, P, I, P]),
+    "sdxl_vae_plan_flops": (C.c_double, [P]),
+    "sdxl_vae_profile_plan": (I, [P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "sdxl_vae_profile_dump": (I, [P, C.c_char_p]),
 }
 
 _lib = None

@@ -46,6 +46,26 @@ TINY_REFINER = UNetConfig(adm_in_channels=16, model_channels=64, channel_mults=(
                           transformer_depths=(0, 1, 1), context_dim=40, is_refiner=True)
 
 
+@dataclass(frozen=True)
+class VaeConfig:
+    """Decoder half of AutoencoderConfig (reference src/model/autoencoder/mod.rs:28-45: the widths are hard-coded
+    there; parameters here so a small instance can be tested) + LatentDecoder.scale_factor."""
+    block_channels: Tuple[Tuple[int, int], ...]
+    latent_channels: int = 4
+    n_group: int = 32
+    scale_factor: float = 0.13025
+
+    @property
+    def upscale(self) -> int:
+        return 2 ** (len(self.block_channels) - 1)
+
+
+# SDXL VAE decoder: DecoderConfig::new(vec![(512,512),(512,512),(512,256),(256,128)], 32)
+SDXL_VAE = VaeConfig(block_channels=((512, 512), (512, 512), (512, 256), (256, 128)))
+# small instance with the same topology rules (3 ResnetBlocks per level, nin_shortcut where widths change)
+TINY_VAE = VaeConfig(block_channels=((128, 128), (128, 64), (64, 64)))
+
+
 @dataclass
 class BlockSpec:
     kind: str              # conv | resnet | downsample | resnet_transformer | resnet_transformer_upsample | resnet_upsample

@@ -20,7 +20,7 @@ import torch
 
 from . import _lib
 from ._lib import SdxlError
-from .config import UNetConfig
+from .config import UNetConfig, VaeConfig
 from .weights import build_pack
 
 
@@ -387,6 +387,80 @@ class Diffuser:
         assert latent_host.device.type == "cpu" and latent_host.dtype == torch.float32 and latent_host.is_contiguous()
         self.ctx.check(self.ctx.lib.sdxl_sampler_step_host(self.h, t, t_prev, latent_host.data_ptr()),
                        "sdxl_sampler_step_host")
+
+
+class LatentDecoder:
+    """Mirror of the reference's LatentDecoder (decode half): `decode_latent` and `latent_to_image`
+    (src/model/stablediffusion/mod.rs:199-237, 263-266) over the device-resident VAE decoder."""
+
+    KIND_NAMES = Diffuser.KIND_NAMES + ["softmax_rows", "transpose_f16", "post_quant"]
+
+    def __init__(self, ctx: Context, cfg: VaeConfig, weights):
+        self.ctx, self.cfg = ctx, cfg
+        pack = weights if isinstance(weights, torch.Tensor) else build_pack(weights)
+        on_device = pack.is_cuda
+        ctx.enter()
+        if on_device:
+            torch.cuda.current_stream(ctx.device).synchronize()
+        cs = _lib.VaeCfg()
+        cs.latent_channels, cs.n_blocks, cs.n_group = cfg.latent_channels, len(cfg.block_channels), cfg.n_group
+        cs.scale_factor = cfg.scale_factor
+        for i, (ci, co) in enumerate(cfg.block_channels):
+            cs.block_in[i], cs.block_out[i] = ci, co
+        h = C.c_void_p()
+        ctx.check(ctx.lib.sdxl_vae_load(ctx.h, C.byref(cs), pack.data_ptr(), pack.numel(), int(on_device), C.byref(h)),
+                  "sdxl_vae_load")
+        self.h = h
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            self.ctx.lib.sdxl_vae_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _prep(self, latent: torch.Tensor):
+        host = not latent.is_cuda
+        latent = latent.to(torch.float32).contiguous()
+        B, _, h, w = latent.shape
+        up = self.cfg.upscale
+        return latent, host, B, h, w, up
+
+    def decode_latent(self, latent: torch.Tensor) -> torch.Tensor:
+        """latent f32 [B,4,h,w] (host or device) -> image f32 [B,3,8h,8w] on the same side."""
+        latent, host, B, h, w, up = self._prep(latent)
+        out = torch.empty((B, 3, h * up, w * up), dtype=torch.float32, device="cpu" if host else self.ctx.device)
+        self.ctx.enter()
+        self.ctx.check(self.ctx.lib.sdxl_vae_decode_latent(self.h, B, h, w, _ptr(latent), int(host), _ptr(out)),
+                       "sdxl_vae_decode_latent")
+        self.ctx.leave()
+        return out
+
+    def latent_to_image(self, latent: torch.Tensor) -> torch.Tensor:
+        """RawImages buffer: u8 [B, 8h, 8w, 3]."""
+        latent, host, B, h, w, up = self._prep(latent)
+        out = torch.empty((B, h * up, w * up, 3), dtype=torch.uint8, device="cpu" if host else self.ctx.device)
+        self.ctx.enter()
+        self.ctx.check(self.ctx.lib.sdxl_vae_latent_to_image(self.h, B, h, w, _ptr(latent), int(host), _ptr(out)),
+                       "sdxl_vae_latent_to_image")
+        self.ctx.leave()
+        return out
+
+    @property
+    def plan_flops(self) -> float:
+        return float(self.ctx.lib.sdxl_vae_plan_flops(self.h))
+
+    def profile_plan(self) -> Dict[str, Dict[str, float]]:
+        ms, fl, ln = (C.c_double * 16)(), (C.c_double * 16)(), (C.c_int * 16)()
+        self.ctx.check(self.ctx.lib.sdxl_vae_profile_plan(self.h, ms, fl, ln), "sdxl_vae_profile_plan")
+        return {n: {"ms": ms[i], "flops": fl[i], "launches": ln[i]} for i, n in enumerate(self.KIND_NAMES) if ln[i]}
+
+    def profile_dump(self, path: str) -> None:
+        self.ctx.check(self.ctx.lib.sdxl_vae_profile_dump(self.h, path.encode()), "sdxl_vae_profile_dump")
 
 
 def ddim_timesteps(n_steps: int, step_start: int = 0, total: int = 1000) -> List[int]:

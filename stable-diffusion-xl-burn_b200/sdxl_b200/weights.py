@@ -21,7 +21,7 @@ from typing import Dict, Iterable, List, Tuple
 import numpy as np
 import torch
 
-from .config import UNetConfig, block_program
+from .config import UNetConfig, VaeConfig, block_program
 
 Spec = Tuple[str, Tuple[int, ...], str, float]  # name, shape, kind, scale
 
@@ -97,18 +97,56 @@ def unet_tensor_specs(cfg: UNetConfig) -> List[Spec]:
     return s
 
 
+def _vres_specs(path: str, c_in: int, c_out: int) -> List[Spec]:
+    s: List[Spec] = [
+        (f"{path}/norm1/weight", (c_in,), "gamma", 1.0), (f"{path}/norm1/bias", (c_in,), "beta", 1.0),
+        (f"{path}/conv1/weight", (c_out, c_in, 3, 3), "conv", 1.0), (f"{path}/conv1/bias", (c_out,), "bias", 1.0),
+        (f"{path}/norm2/weight", (c_out,), "gamma", 1.0), (f"{path}/norm2/bias", (c_out,), "beta", 1.0),
+        (f"{path}/conv2/weight", (c_out, c_out, 3, 3), "conv", RESID_SCALE), (f"{path}/conv2/bias", (c_out,), "bias", 1.0),
+    ]
+    if c_in != c_out:
+        s += [(f"{path}/nin_shortcut/weight", (c_out, c_in, 1, 1), "conv", 1.0),
+              (f"{path}/nin_shortcut/bias", (c_out,), "bias", 1.0)]
+    return s
+
+
+def vae_decoder_tensor_specs(cfg: VaeConfig) -> List[Spec]:
+    """Decoder-side tensors of the autoencoder dump tree (reference src/model/autoencoder/load.rs:17-76, 107-114)."""
+    cl, c0 = cfg.latent_channels, cfg.block_channels[0][0]
+    s: List[Spec] = [
+        ("post_quant_conv/weight", (cl, cl, 1, 1), "conv", 1.0), ("post_quant_conv/bias", (cl,), "bias", 1.0),
+        ("decoder/conv_in/weight", (c0, cl, 3, 3), "conv", 1.0), ("decoder/conv_in/bias", (c0,), "bias", 1.0),
+    ]
+    s += _vres_specs("decoder/mid/block_1", c0, c0)
+    s += [("decoder/mid/attn/norm/weight", (c0,), "gamma", 1.0), ("decoder/mid/attn/norm/bias", (c0,), "beta", 1.0)]
+    for n, sc in (("q", 1.0), ("k", 1.0), ("v", 1.0), ("proj_out", RESID_SCALE)):
+        s += [(f"decoder/mid/attn/{n}/weight", (c0, c0, 1, 1), "conv", sc), (f"decoder/mid/attn/{n}/bias", (c0,), "bias", 1.0)]
+    s += _vres_specs("decoder/mid/block_2", c0, c0)
+    for i, (ci, co) in enumerate(cfg.block_channels):
+        b = f"decoder/blocks/{i}"
+        s += _vres_specs(f"{b}/res1", ci, co) + _vres_specs(f"{b}/res2", co, co) + _vres_specs(f"{b}/res3", co, co)
+        if i != len(cfg.block_channels) - 1:
+            s += [(f"{b}/upsampler/weight", (co, co, 3, 3), "conv", 1.0), (f"{b}/upsampler/bias", (co,), "bias", 1.0)]
+    cf = cfg.block_channels[-1][1]
+    s += [("decoder/norm_out/weight", (cf,), "gamma", 1.0), ("decoder/norm_out/bias", (cf,), "beta", 1.0),
+          ("decoder/conv_out/weight", (3, cf, 3, 3), "conv", 1.0), ("decoder/conv_out/bias", (3,), "bias", 1.0)]
+    return s
+
+
 def alphas_cumprod(n_steps: int = 1000) -> torch.Tensor:
     """LegacyDDPMDiscretization: scaled-linear betas 0.00085 -> 0.012 (reference python/dump.py:29-36)."""
     betas = np.linspace(0.00085 ** 0.5, 0.012 ** 0.5, n_steps, dtype=np.float64) ** 2
     return torch.from_numpy(np.cumprod(1.0 - betas, axis=0)).to(torch.float16)
 
 
-def synth_weights(cfg: UNetConfig, seed: int = 0, device: str = "cpu") -> Dict[str, torch.Tensor]:
-    """Deterministic (per device type) synthetic f16 weights, reference layouts and names."""
+def synth_weights(cfg, seed: int = 0, device: str = "cpu") -> Dict[str, torch.Tensor]:
+    """Deterministic (per device type) synthetic f16 weights, reference layouts and names.
+    cfg: UNetConfig (adds alphas_cumprod) or VaeConfig (decoder tensors)."""
     gen = torch.Generator(device=device)
     gen.manual_seed(seed)
     out: Dict[str, torch.Tensor] = {}
-    for name, shape, kind, scale in unet_tensor_specs(cfg):
+    is_vae = isinstance(cfg, VaeConfig)
+    for name, shape, kind, scale in (vae_decoder_tensor_specs(cfg) if is_vae else unet_tensor_specs(cfg)):
         if kind == "linear":
             t = torch.randn(shape, generator=gen, device=device) * (scale / shape[0] ** 0.5)
         elif kind == "conv":
@@ -122,7 +160,8 @@ def synth_weights(cfg: UNetConfig, seed: int = 0, device: str = "cpu") -> Dict[s
         else:
             raise ValueError(kind)
         out[name] = t.to(torch.float16)
-    out["alphas_cumprod"] = alphas_cumprod(cfg.n_steps).to(device)
+    if not is_vae:
+        out["alphas_cumprod"] = alphas_cumprod(cfg.n_steps).to(device)
     return out
 
 

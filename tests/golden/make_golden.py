@@ -5,7 +5,8 @@ Method = the reference's own tiny-model probe (src/bin/test/main.rs:51-54,128-14
 arb_tensor(dims) = sin(arange(prod(dims))) inputs through a tiny UNet. Weights are the seeded synthetic
 set (sdxl_b200.synth_weights(TINY, seed=0), CPU generator => identical on every machine of this image).
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py          # everything
+    python tests/golden/make_golden.py vae      # only the latent-decoder fixture
 """
 import os
 import sys
@@ -17,7 +18,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "stable-diffusion-xl-burn_b200"))
 from oracle import unet_oracle as O  # noqa: E402
-from sdxl_b200.config import TINY  # noqa: E402
+from oracle import vae_oracle as VO  # noqa: E402
+from sdxl_b200.config import TINY, TINY_VAE  # noqa: E402
 from sdxl_b200.weights import alphas_cumprod, synth_weights  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -31,8 +33,21 @@ def h16f(t):
     return t.to(torch.float16).float()
 
 
+def vae():
+    """Latent decoder (oracle/vae_oracle.py): TINY_VAE, latent = 0.13025 * 2 * sin(arange) at 8x8, B=2 -> image f32 + u8."""
+    w = O.to_f32(synth_weights(TINY_VAE, seed=0))
+    latent = arb(2, 4, 8, 8) * (2 * TINY_VAE.scale_factor)
+    img = VO.decode_latent(TINY_VAE, w, latent)
+    u8 = VO.latent_to_image(TINY_VAE, w, latent)
+    np.savez(os.path.join(HERE, "tiny_vae_decode.npz"), latent=latent.numpy(), image=img.numpy(), u8=u8.numpy())
+    print("tiny_vae_decode", img.shape, float(img.abs().mean()), float(u8.float().mean()))
+
+
 def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
+    if "vae" in sys.argv[1:]:
+        return vae()
+    vae()
     w = O.to_f32(synth_weights(TINY, seed=0))
     # 1) the reference's probe shapes: x[1,4,4,4], context[1,1,ctx], y[1,adm], t=[1]
     for tag, (B, h, wd, n_ctx, t) in {"": (1, 4, 4, 1, 1), "_16": (2, 16, 16, 77, 749)}.items():

@@ -1,0 +1,118 @@
+"""GPU parity of the latent decoder (LatentDecoder::{decode_latent, latent_to_image}) against the CPU f32 oracle,
+through the C ABI (sdxl_b200.LatentDecoder -> libsdxl_b200.so).
+
+Tolerance statement. The reference runs the autoencoder in f32. The engine keeps the residual stream, GroupNorm
+statistics, the attention scores and the softmax in f32 but rounds every tensor-core operand (normalised activations,
+weights, attention probabilities) to f16, as on the UNet path; weights are the same f16-stored values in both. The
+difference is operand rounding (2^-11 relative per GEMM input), measured as relative L2 error ||a-b|| / ||b||:
+  * decode_latent:        <= 2e-3
+  * latent_to_image (u8): |a-b| <= 1 everywhere, equal on >= 95 % of the bytes (an f32 error of ~1e-3 * 127.5 moves
+    a value across a truncation boundary with that probability; measured 97.6 %)
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from sdxl_b200 import SDXL_VAE, TINY_VAE, LatentDecoder, synth_weights
+from oracle import unet_oracle as O
+from oracle import vae_oracle as VO
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 2e-3
+
+
+def rel_err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+@pytest.fixture(scope="module")
+def tiny(ctx):
+    w = synth_weights(TINY_VAE, seed=0)
+    d = LatentDecoder(ctx, TINY_VAE, w)
+    yield d, O.to_f32(w)
+    d.close()
+
+
+def test_golden_fixture(tiny):
+    d, _ = tiny
+    g = np.load(os.path.join(GOLD, "tiny_vae_decode.npz"))
+    lat = torch.from_numpy(g["latent"])
+    img = d.decode_latent(lat)                       # host in -> host out
+    assert not img.is_cuda
+    e = rel_err(img, torch.from_numpy(g["image"]))
+    print("golden decode rel err", e)
+    assert e <= TOL
+    u8 = d.latent_to_image(lat.cuda()).cpu().numpy().astype(np.int32)   # device in -> device out
+    diff = np.abs(u8 - g["u8"].astype(np.int32))
+    assert diff.max() <= 1 and (diff == 0).mean() >= 0.95
+
+
+@pytest.mark.parametrize("B,h,w", [(1, 8, 8), (2, 8, 16), (3, 16, 16), (1, 24, 8)])
+def test_decode_vs_oracle(tiny, B, h, w):
+    d, wf = tiny
+    lat = torch.randn(B, 4, h, w, generator=torch.Generator().manual_seed(10 * B + h)) * TINY_VAE.scale_factor * 1.5
+    got = d.decode_latent(lat.cuda())
+    want = VO.decode_latent(TINY_VAE, wf, lat)
+    e = rel_err(got, want)
+    print(f"tiny decode B={B} {h}x{w}: rel err {e:.2e}")
+    assert got.shape == (B, 3, 4 * h, 4 * w) and e <= TOL
+    assert abs(d.plan_flops / VO.decoder_flops(TINY_VAE, h, w, B) - 1) < 1e-9
+
+
+def test_bad_shape_is_an_error(tiny):
+    d, _ = tiny
+    with pytest.raises(Exception, match="multiple of 64"):
+        d.decode_latent(torch.zeros(1, 4, 4, 4))
+
+
+def test_batch_invariance_and_determinism(tiny):
+    d, _ = tiny
+    lat = torch.randn(1, 4, 8, 8, generator=torch.Generator().manual_seed(5)).cuda() * 0.2
+    a = d.decode_latent(lat)
+    b = d.decode_latent(torch.cat([lat, lat * 0.5, lat]))
+    assert torch.equal(a[0], b[0]) and torch.equal(b[0], b[2])
+    assert torch.equal(a, d.decode_latent(lat))
+
+
+@pytest.fixture(scope="module")
+def full(ctx):
+    w = synth_weights(SDXL_VAE, seed=7)
+    d = LatentDecoder(ctx, SDXL_VAE, w)
+    yield d, w
+    d.close()
+
+
+def test_sdxl_vae_256_vs_oracle(full):
+    """Real widths (512/512/256/128) at a 256^2 image (latent 32^2, T=1024): the oracle finishes in seconds."""
+    d, w = full
+    torch.set_num_threads(min(32, os.cpu_count() or 1))
+    lat = torch.randn(1, 4, 32, 32, generator=torch.Generator().manual_seed(0)) * SDXL_VAE.scale_factor
+    got = d.decode_latent(lat.cuda())
+    want = VO.decode_latent(SDXL_VAE, O.to_f32(w), lat)
+    e = rel_err(got, want)
+    print("SDXL VAE 256^2 decode rel err", e)
+    assert e <= TOL
+    u8 = d.latent_to_image(lat.cuda()).cpu().numpy().astype(np.int32)
+    ref = VO.latent_to_image(SDXL_VAE, O.to_f32(w), lat).numpy().astype(np.int32)
+    diff = np.abs(u8 - ref)
+    assert diff.max() <= 1 and (diff == 0).mean() >= 0.95
+
+
+def test_sdxl_vae_1024_properties(full):
+    """Full size (latent 128^2, T=16384, 1.07 GB score matrix): size-independent properties — determinism, finiteness,
+    the FLOP total of SURVEY.md §8(f), u8 conversion consistent with the f32 image, batch invariance."""
+    d, _ = full
+    lat = torch.randn(1, 4, 128, 128, generator=torch.Generator().manual_seed(1)).cuda() * SDXL_VAE.scale_factor
+    a = d.decode_latent(lat)
+    assert a.shape == (1, 3, 1024, 1024) and torch.isfinite(a).all()
+    assert abs(d.plan_flops / 10.470392594432e12 - 1) < 1e-9
+    assert torch.equal(a, d.decode_latent(lat))
+    u8 = d.latent_to_image(lat)
+    ref = (((a.permute(0, 2, 3, 1) + 1.0) / 2.0) * 255.0).clamp(0, 255).to(torch.uint8)
+    assert torch.equal(u8, ref)
+    b = d.decode_latent(torch.cat([lat, lat]))
+    assert torch.equal(b[0], a[0]) and torch.equal(b[1], a[0])
