@@ -224,6 +224,32 @@ SDXL_API double sdxl_vae_plan_flops(const sdxl_vae* vae);
 SDXL_API int sdxl_vae_profile_plan(sdxl_vae* vae, double* ms_by_kind, double* flops_by_kind, int* launches_by_kind);
 SDXL_API int sdxl_vae_profile_dump(sdxl_vae* vae, const char* path);
 
+/* ------------------------------------------------------------------------------------------------
+ * BPE tokenizers of the Embedder. CPU host code, no device work, no sdxl_ctx.
+ * Replaces ClipTokenizer (reference src/token/clip.rs:80-230), OpenClipTokenizer (src/token/open_clip.rs:71-221) and
+ * tokenize_text (src/model/stablediffusion/mod.rs:778-793). The vocabulary files are the reference's own
+ * (tokenizer/clip/bpe_simple_vocab_16e6.txt; tokenizer/open_clip/{merges,vocab}.txt), passed by path. Token ids are
+ * bit-exact with the reference (known-answer vector src/token/clip.rs:232-249). Errors: non-zero status,
+ * text in sdxl_tokenizer_last_error() (thread-local); where the reference would panic (piece not in the vocabulary)
+ * an error is returned instead.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct sdxl_tokenizer sdxl_tokenizer;
+SDXL_API const char* sdxl_tokenizer_last_error(void);
+/* == ClipTokenizer::new (clip.rs:91-122); pads with <|endoftext|> (49407) */
+SDXL_API int sdxl_tokenizer_create_clip(const char* merges_path, sdxl_tokenizer** out);
+/* == OpenClipTokenizer::new (open_clip.rs:82-113); pads with 0 */
+SDXL_API int sdxl_tokenizer_create_open_clip(const char* merges_path, const char* vocab_path, sdxl_tokenizer** out);
+SDXL_API void sdxl_tokenizer_destroy(sdxl_tokenizer* tok);
+/* == Tokenizer::encode(text, add_sot, add_eot) (clip.rs:181-205). ids_out may be NULL to query *n_out. */
+SDXL_API int sdxl_tokenizer_encode(const sdxl_tokenizer* tok, const char* text_utf8, int add_sot, int add_eot,
+                                   uint32_t* ids_out, int capacity, int* n_out);
+/* == Tokenizer::decode (clip.rs:207-213); NUL-terminated UTF-8, *n_out = length without the NUL. */
+SDXL_API int sdxl_tokenizer_decode(const sdxl_tokenizer* tok, const uint32_t* ids, int n, char* out, int capacity, int* n_out);
+/* == tokenize_text (stablediffusion/mod.rs:778-793): encode(text, true, true) resized to seq_len with the padding token. */
+SDXL_API int sdxl_tokenize_text(const sdxl_tokenizer* tok, const char* text_utf8, int seq_len, int32_t* tokens_out);
+/* start_of_text_token / end_of_text_token / padding_token (clip.rs:215-229) */
+SDXL_API int sdxl_tokenizer_special(const sdxl_tokenizer* tok, uint32_t* sot, uint32_t* eot, uint32_t* pad);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,8 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "sdxl_b200", "libsdxl_b200.so")
-SOURCES = ["igemm.cu", "attention.cu", "norm.cu", "elementwise.cu", "vae_kernels.cu", "engine.cu"]
-HEADERS = ["common.cuh", "kernels.h", os.path.join("..", "..", "include", "sdxl_b200.h")]
+SOURCES = ["igemm.cu", "attention.cu", "norm.cu", "elementwise.cu", "vae_kernels.cu", "engine.cu", "tokenizer.cpp"]
+HEADERS = ["common.cuh", "kernels.h", "unicode_tables.h", os.path.join("..", "..", "include", "sdxl_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -41,7 +41,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         return LIB
 
     def cc(src: str) -> str:
-        obj = os.path.join(BUILD, src.replace(".cu", ".o"))
+        obj = os.path.join(BUILD, os.path.splitext(src)[0] + ".o")
         cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd), file=sys.stderr)

@@ -90,6 +90,14 @@ PROTOTYPES = {
     "sdxl_vae_plan_flops": (C.c_double, [P]),
     "sdxl_vae_profile_plan": (I, [P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "sdxl_vae_profile_dump": (I, [P, C.c_char_p]),
+    "sdxl_tokenizer_last_error": (C.c_char_p, []),
+    "sdxl_tokenizer_create_clip": (I, [C.c_char_p, C.POINTER(P)]),
+    "sdxl_tokenizer_create_open_clip": (I, [C.c_char_p, C.c_char_p, C.POINTER(P)]),
+    "sdxl_tokenizer_destroy": (None, [P]),
+    "sdxl_tokenizer_encode": (I, [P, C.c_char_p, I, I, C.POINTER(C.c_uint32), I, C.POINTER(I)]),
+    "sdxl_tokenizer_decode": (I, [P, C.POINTER(C.c_uint32), I, C.c_char_p, I, C.POINTER(I)]),
+    "sdxl_tokenize_text": (I, [P, C.c_char_p, I, C.POINTER(C.c_int32)]),
+    "sdxl_tokenizer_special": (I, [P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
 }
 
 _lib = None
