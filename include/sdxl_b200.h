@@ -162,8 +162,10 @@ SDXL_API int sdxl_randn(sdxl_ctx* ctx, float* out, size_t n, uint64_t seed, uint
 
 /* ---- operator level (== the burn ops / Backend hooks the hot path is built from) ------------ */
 /* == Backend::qkv_attention (src/backend.rs:4-10, libtorch impl :32-79, generic :88-128).
- * q [B,T,C], k/v [B,S,C] f16, C = n_head*64, mask must be NULL (the UNet never passes one,
- * unet/mod.rs:1017). out [B,T,C] f16. */
+ * q [B,T,C], k/v [B,S,C] f16, C = n_head*64, out [B,T,C] f16. mask: NULL (UNet, unet/mod.rs:1017: tensor-core
+ * flash kernel) or an additive f16 [T,S] matrix such as attn_decoder_mask (text encoders, clip/mod.rs:88: short
+ * sequences, CUDA-core kernel). The VAE's single-head d=512 call (autoencoder/mod.rs:572) is served inside
+ * sdxl_vae_decode_latent, not here. */
 SDXL_API int sdxl_qkv_attention(sdxl_ctx* ctx, const sdxl_half* q, const sdxl_half* k, const sdxl_half* v,
                        const sdxl_half* mask, int B, int T, int S, int C, int n_head, sdxl_half* out);
 /* == nn::Linear::forward: x [M,K] f16, w [K,N] f16 ([in,out], python/save.py:20-25), bias [N] f16 or
@@ -249,6 +251,36 @@ SDXL_API int sdxl_tokenizer_decode(const sdxl_tokenizer* tok, const uint32_t* id
 SDXL_API int sdxl_tokenize_text(const sdxl_tokenizer* tok, const char* text_utf8, int seq_len, int32_t* tokens_out);
 /* start_of_text_token / end_of_text_token / padding_token (clip.rs:215-229) */
 SDXL_API int sdxl_tokenizer_special(const sdxl_tokenizer* tok, uint32_t* sot, uint32_t* eot, uint32_t* pad);
+
+/* ------------------------------------------------------------------------------------------------
+ * Text encoders of the Embedder: replaces CLIP::{forward_hidden, forward_hidden_pooled}
+ * (reference src/model/clip/mod.rs:82-147) for both CLIP-L and OpenCLIP-bigG. Weight names follow
+ * load_clip_text_transformer (src/model/clip/load.rs:79-115): token_embedding/weight [n_vocab,n_state],
+ * position_embedding/weight [n_ctx,n_state], blocks/<i>/{attn_ln,mlp_ln}/{weight,bias},
+ * blocks/<i>/attn/{query,key,value,out}/{weight [in,out],bias}, blocks/<i>/mlp/{fc1,fc2}/{weight,bias},
+ * layer_norm/{weight,bias}, text_projection [n_state,embed_dim] (optional); all f16 in the pack.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct sdxl_clip sdxl_clip;
+typedef struct sdxl_clip_cfg {          /* == CLIPConfig (clip/mod.rs:18-26) */
+  int32_t n_vocab;                      /* 49408 */
+  int32_t n_state;                      /* 768 CLIP-L, 1280 OpenCLIP-bigG */
+  int32_t embed_dim;                    /* 768 / 1280 */
+  int32_t n_head;                       /* 12 / 20 (head dim 64) */
+  int32_t n_ctx;                        /* 77 */
+  int32_t n_layer;                      /* 12 / 32 */
+  int32_t quick_gelu;                   /* 1 CLIP-L (QuickGELU), 0 OpenCLIP (erf GELU) */
+} sdxl_clip_cfg;
+SDXL_API int sdxl_clip_load(sdxl_ctx* ctx, const sdxl_clip_cfg* cfg, const void* pack, size_t bytes, int pack_on_device,
+                            sdxl_clip** out);
+SDXL_API void sdxl_clip_destroy(sdxl_clip* clip);
+/* == CLIP::forward_hidden(tokens [B,n_ctx], hidden_idx): the stream after blocks[0..hidden_idx], f32 [B,n_ctx,n_state].
+ * tokens are host int32 (tokenize_text output); the causal mask is applied as attn_decoder_mask does (backend.rs:21). */
+SDXL_API int sdxl_clip_forward_hidden(sdxl_clip* clip, int B, const int32_t* tokens_host, int hidden_idx, float* hidden_out,
+                                      int out_on_host);
+/* == CLIP::forward_hidden_pooled: hidden as above plus pooled [B,embed_dim] = layer_norm(x_final)[b, argmax(tokens[b])] @ text_projection */
+SDXL_API int sdxl_clip_forward_hidden_pooled(sdxl_clip* clip, int B, const int32_t* tokens_host, int hidden_idx,
+                                             float* hidden_out, float* pooled_out, int out_on_host);
+SDXL_API double sdxl_clip_plan_flops(const sdxl_clip* clip);
 
 #ifdef __cplusplus
 }

@@ -205,6 +205,20 @@ int post_quant_launch(cudaStream_t st, const float* x, int B, int C, int HW, con
 // u8[b,p,c] = trunc(clamp(((x+1)/2)*255, 0, 255)), c < 3, from NHWC f32 [npix, ldx].
 int image_u8_launch(cudaStream_t st, const float* x, long npix, int ldx, uint8_t* out);
 
+// Text-encoder kernels (clip_kernels.cu)
+// x[b*T+t,:] = tok_emb[tokens[b,t],:] + pos_emb[t,:] (f16 tables -> f32); *err is set to 1 on an id outside [0, n_vocab).
+int embed_tokens_launch(cudaStream_t st, const int* tokens, int rows, int T, int C, int n_vocab, const __half* tok_emb,
+                        const __half* pos_emb, float* x, int* err);
+// Masked attention for short sequences, head dim 64: additive f16 mask [T,S] (nullable) and/or causal (key <= query).
+int attention_small_launch(cudaStream_t st, const __half* q, int q_pitch, int q_col0, const __half* k, const __half* v,
+                           int kv_pitch, int k_col0, int v_col0, int B, int T, int S, int n_head, const __half* mask,
+                           int causal, __half* out, int ldo);
+// y = gelu_erf(x) (quick = 0) or x * sigmoid(1.702 x) (quick = 1); f32 -> f16, n % 4 == 0.
+int mlp_act_launch(cudaStream_t st, const float* x, size_t n, int quick, __half* y);
+// y[b,:] = LayerNorm(x[b*T + idx[b], :]) in f32.
+int ln_gather_f32_launch(cudaStream_t st, const float* x, const int* idx, int B, int T, int C, const float* gamma,
+                         const float* beta, float eps, float* y);
+
 // Weight re-layout at load time (elementwise.cu)
 // Linear [K(in), N(out)] row-major f16 -> K-major [N, Kpad] f16 (zero padded), dst row pitch Kpad;
 // rows written at dst_row0 + perm(n) where perm handles the GEGLU value/gate interleave (geglu_bn>0).

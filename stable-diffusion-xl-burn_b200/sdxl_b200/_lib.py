@@ -50,6 +50,10 @@ class VaeCfg(C.Structure):
     ]
 
 
+class ClipCfg(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n_vocab", "n_state", "embed_dim", "n_head", "n_ctx", "n_layer", "quick_gelu")]
+
+
 # name -> (restype, argtypes); every symbol include/sdxl_b200.h declares
 P = C.c_void_p
 I = C.c_int
@@ -98,6 +102,11 @@ PROTOTYPES = {
     "sdxl_tokenizer_decode": (I, [P, C.POINTER(C.c_uint32), I, C.c_char_p, I, C.POINTER(I)]),
     "sdxl_tokenize_text": (I, [P, C.c_char_p, I, C.POINTER(C.c_int32)]),
     "sdxl_tokenizer_special": (I, [P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "sdxl_clip_load": (I, [P, C.POINTER(ClipCfg), P, C.c_size_t, I, C.POINTER(P)]),
+    "sdxl_clip_destroy": (None, [P]),
+    "sdxl_clip_forward_hidden": (I, [P, I, C.POINTER(C.c_int32), I, P, I]),
+    "sdxl_clip_forward_hidden_pooled": (I, [P, I, C.POINTER(C.c_int32), I, P, P, I]),
+    "sdxl_clip_plan_flops": (C.c_double, [P]),
 }
 
 _lib = None

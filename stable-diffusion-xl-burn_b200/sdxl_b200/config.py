@@ -66,6 +66,26 @@ SDXL_VAE = VaeConfig(block_channels=((512, 512), (512, 512), (512, 256), (256, 1
 TINY_VAE = VaeConfig(block_channels=((128, 128), (128, 64), (64, 64)))
 
 
+@dataclass(frozen=True)
+class ClipConfig:
+    """== CLIPConfig (reference src/model/clip/mod.rs:18-26)."""
+    n_vocab: int
+    n_state: int
+    embed_dim: int
+    n_head: int
+    n_ctx: int
+    n_layer: int
+    quick_gelu: bool
+
+
+# SDXL's two text encoders (SURVEY.md §8(f): CLIP ViT-L/14 text tower, OpenCLIP ViT-bigG/14 text tower)
+SDXL_CLIP_L = ClipConfig(n_vocab=49408, n_state=768, embed_dim=768, n_head=12, n_ctx=77, n_layer=12, quick_gelu=True)
+SDXL_OPEN_CLIP_G = ClipConfig(n_vocab=49408, n_state=1280, embed_dim=1280, n_head=20, n_ctx=77, n_layer=32, quick_gelu=False)
+# small instances for known-answer tests (vocabulary sized for tests/golden/mini_bpe plus the hard-coded 49406/49407)
+TINY_CLIP = ClipConfig(n_vocab=49408, n_state=128, embed_dim=128, n_head=2, n_ctx=77, n_layer=3, quick_gelu=True)
+TINY_OPEN_CLIP = ClipConfig(n_vocab=49408, n_state=192, embed_dim=64, n_head=3, n_ctx=77, n_layer=4, quick_gelu=False)
+
+
 @dataclass
 class BlockSpec:
     kind: str              # conv | resnet | downsample | resnet_transformer | resnet_transformer_upsample | resnet_upsample

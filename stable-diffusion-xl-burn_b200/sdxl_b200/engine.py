@@ -77,15 +77,18 @@ class Context:
     # ---- operator level ------------------------------------------------------------------------
     def qkv_attention(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mask: Optional[torch.Tensor],
                       n_head: int) -> torch.Tensor:
-        """== Backend::qkv_attention (src/backend.rs:4-10). q [B,T,C], k/v [B,S,C] f16."""
-        if mask is not None:
-            raise SdxlError("qkv_attention: mask is not supported on the UNet path")
+        """== Backend::qkv_attention (src/backend.rs:4-10). q [B,T,C], k/v [B,S,C] f16; mask: additive [T,S] (the text
+        encoders' decoder mask) or None (UNet / VAE)."""
         B, T, Cc = q.shape
         S = k.shape[1]
         q, k, v = (t.to(self.device, torch.float16).contiguous() for t in (q, k, v))
+        if mask is not None:
+            if tuple(mask.shape) != (T, S):
+                raise SdxlError(f"qkv_attention: mask must be [{T},{S}], got {tuple(mask.shape)}")
+            mask = mask.to(self.device, torch.float16).contiguous()
         out = torch.empty_like(q)
         self.enter()
-        self.check(self.lib.sdxl_qkv_attention(self.h, _ptr(q), _ptr(k), _ptr(v), None, B, T, S, Cc, n_head, _ptr(out)),
+        self.check(self.lib.sdxl_qkv_attention(self.h, _ptr(q), _ptr(k), _ptr(v), _ptr(mask), B, T, S, Cc, n_head, _ptr(out)),
                    "sdxl_qkv_attention")
         self.leave()
         return out

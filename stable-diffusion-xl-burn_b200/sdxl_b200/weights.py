@@ -21,7 +21,7 @@ from typing import Dict, Iterable, List, Tuple
 import numpy as np
 import torch
 
-from .config import UNetConfig, VaeConfig, block_program
+from .config import ClipConfig, UNetConfig, VaeConfig, block_program
 
 Spec = Tuple[str, Tuple[int, ...], str, float]  # name, shape, kind, scale
 
@@ -133,6 +133,24 @@ def vae_decoder_tensor_specs(cfg: VaeConfig) -> List[Spec]:
     return s
 
 
+def clip_tensor_specs(cfg: ClipConfig) -> List[Spec]:
+    """Text-encoder tensors of the dump tree (reference src/model/clip/load.rs:15-115)."""
+    c = cfg.n_state
+    s: List[Spec] = [("token_embedding/weight", (cfg.n_vocab, c), "embed", 1.0),
+                     ("position_embedding/weight", (cfg.n_ctx, c), "embed", 0.5)]
+    for i in range(cfg.n_layer):
+        b = f"blocks/{i}"
+        for n in ("attn_ln", "mlp_ln"):
+            s += [(f"{b}/{n}/weight", (c,), "gamma", 1.0), (f"{b}/{n}/bias", (c,), "beta", 1.0)]
+        for n, sc in (("query", 1.0), ("key", 1.0), ("value", 1.0), ("out", RESID_SCALE)):
+            s += [(f"{b}/attn/{n}/weight", (c, c), "linear", sc), (f"{b}/attn/{n}/bias", (c,), "bias", 1.0)]
+        s += [(f"{b}/mlp/fc1/weight", (c, 4 * c), "linear", 1.0), (f"{b}/mlp/fc1/bias", (4 * c,), "bias", 1.0),
+              (f"{b}/mlp/fc2/weight", (4 * c, c), "linear", RESID_SCALE), (f"{b}/mlp/fc2/bias", (c,), "bias", 1.0)]
+    s += [("layer_norm/weight", (c,), "gamma", 1.0), ("layer_norm/bias", (c,), "beta", 1.0),
+          ("text_projection", (c, cfg.embed_dim), "linear", 1.0)]
+    return s
+
+
 def alphas_cumprod(n_steps: int = 1000) -> torch.Tensor:
     """LegacyDDPMDiscretization: scaled-linear betas 0.00085 -> 0.012 (reference python/dump.py:29-36)."""
     betas = np.linspace(0.00085 ** 0.5, 0.012 ** 0.5, n_steps, dtype=np.float64) ** 2
@@ -141,12 +159,14 @@ def alphas_cumprod(n_steps: int = 1000) -> torch.Tensor:
 
 def synth_weights(cfg, seed: int = 0, device: str = "cpu") -> Dict[str, torch.Tensor]:
     """Deterministic (per device type) synthetic f16 weights, reference layouts and names.
-    cfg: UNetConfig (adds alphas_cumprod) or VaeConfig (decoder tensors)."""
+    cfg: UNetConfig (adds alphas_cumprod), VaeConfig (decoder tensors) or ClipConfig (text encoder)."""
     gen = torch.Generator(device=device)
     gen.manual_seed(seed)
     out: Dict[str, torch.Tensor] = {}
     is_vae = isinstance(cfg, VaeConfig)
-    for name, shape, kind, scale in (vae_decoder_tensor_specs(cfg) if is_vae else unet_tensor_specs(cfg)):
+    is_clip = isinstance(cfg, ClipConfig)
+    specs = vae_decoder_tensor_specs(cfg) if is_vae else clip_tensor_specs(cfg) if is_clip else unet_tensor_specs(cfg)
+    for name, shape, kind, scale in specs:
         if kind == "linear":
             t = torch.randn(shape, generator=gen, device=device) * (scale / shape[0] ** 0.5)
         elif kind == "conv":
@@ -157,10 +177,12 @@ def synth_weights(cfg, seed: int = 0, device: str = "cpu") -> Dict[str, torch.Te
             t = 1.0 + torch.randn(shape, generator=gen, device=device) * 0.05
         elif kind == "beta":
             t = torch.randn(shape, generator=gen, device=device) * 0.05
+        elif kind == "embed":
+            t = torch.randn(shape, generator=gen, device=device) * scale
         else:
             raise ValueError(kind)
         out[name] = t.to(torch.float16)
-    if not is_vae:
+    if not is_vae and not is_clip:
         out["alphas_cumprod"] = alphas_cumprod(cfg.n_steps).to(device)
     return out
 

@@ -7,6 +7,7 @@ set (sdxl_b200.synth_weights(TINY, seed=0), CPU generator => identical on every 
 
     python tests/golden/make_golden.py          # everything
     python tests/golden/make_golden.py vae      # only the latent-decoder fixture
+    python tests/golden/make_golden.py clip     # only the text-encoder fixture
 """
 import os
 import sys
@@ -19,7 +20,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "stable-diffusion-xl-burn_b200"))
 from oracle import unet_oracle as O  # noqa: E402
 from oracle import vae_oracle as VO  # noqa: E402
-from sdxl_b200.config import TINY, TINY_VAE  # noqa: E402
+from oracle import clip_oracle as CO  # noqa: E402
+from sdxl_b200.config import TINY, TINY_CLIP, TINY_OPEN_CLIP, TINY_VAE  # noqa: E402
 from sdxl_b200.weights import alphas_cumprod, synth_weights  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -43,11 +45,28 @@ def vae():
     print("tiny_vae_decode", img.shape, float(img.abs().mean()), float(u8.float().mean()))
 
 
+def clip():
+    """Text encoders (oracle/clip_oracle.py): TINY_CLIP forward_hidden (penultimate) and TINY_OPEN_CLIP forward_hidden_pooled on
+    two fixed token rows (CLIP-style end-of-text padding and OpenCLIP-style zero padding)."""
+    rows = [[49406, 320, 1125, 539, 320, 2368, 49407], [49406, 17, 4, 256, 300, 301, 302, 303, 9, 49407]]
+    t1 = torch.tensor([r + [49407] * (77 - len(r)) for r in rows])
+    t2 = torch.tensor([r + [0] * (77 - len(r)) for r in rows])
+    w1, w2 = O.to_f32(synth_weights(TINY_CLIP, seed=1)), O.to_f32(synth_weights(TINY_OPEN_CLIP, seed=2))
+    h1 = CO.forward_hidden(TINY_CLIP, w1, t1, TINY_CLIP.n_layer - 1)
+    h2, p2 = CO.forward_hidden_pooled(TINY_OPEN_CLIP, w2, t2, TINY_OPEN_CLIP.n_layer - 1)
+    np.savez(os.path.join(HERE, "tiny_clip.npz"), tokens_clip=t1.numpy().astype(np.int32), tokens_open_clip=t2.numpy().astype(np.int32),
+             hidden_clip=h1.numpy(), hidden_open_clip=h2.numpy(), pooled_open_clip=p2.numpy())
+    print("tiny_clip", h1.shape, float(h1.abs().mean()), h2.shape, float(p2.abs().mean()))
+
+
 def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     if "vae" in sys.argv[1:]:
         return vae()
+    if "clip" in sys.argv[1:]:
+        return clip()
     vae()
+    clip()
     w = O.to_f32(synth_weights(TINY, seed=0))
     # 1) the reference's probe shapes: x[1,4,4,4], context[1,1,ctx], y[1,adm], t=[1]
     for tag, (B, h, wd, n_ctx, t) in {"": (1, 4, 4, 1, 1), "_16": (2, 16, 16, 77, 749)}.items():

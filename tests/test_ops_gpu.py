@@ -133,11 +133,17 @@ def test_qkv_attention_large_dynamic_range(ctx, scale):
     assert rel_err(out, ref) < 2e-3
 
 
-def test_qkv_attention_rejects_mask(ctx):
+def test_qkv_attention_mask_shape_is_checked(ctx):
     from sdxl_b200 import SdxlError
     q = torch.zeros(1, 8, 64, dtype=torch.float16)
     with pytest.raises(SdxlError):
-        ctx.qkv_attention(q, q, q, torch.zeros(8, 8), 1)
+        ctx.qkv_attention(q, q, q, torch.zeros(4, 8), 1)
+    # an all-zero additive mask is the unmasked result (short-sequence kernel vs tensor-core kernel)
+    g = torch.Generator().manual_seed(0)
+    q, k, v = (torch.randn(2, 40, 128, generator=g).half() for _ in range(3))
+    a = ctx.qkv_attention(q, k, v, torch.zeros(40, 40), 2)
+    b = ctx.qkv_attention(q, k, v, None, 2)
+    assert rel_err(a, b) < 2e-3
 
 
 def test_timestep_embedding(ctx):
