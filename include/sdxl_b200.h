@@ -208,6 +208,11 @@ typedef struct sdxl_vae_cfg {
   int32_t block_out[SDXL_MAX_LEVELS];   /* 512, 512, 256, 128 */
   int32_t n_group;                      /* 32 */
   double scale_factor;                  /* 0.13025 for SDXL (stablediffusion/load.rs:78) */
+  /* encoder half (EncoderConfig, autoencoder/mod.rs:30-31); n_enc_blocks = 0: decoder only, encoder tensors not read */
+  int32_t n_enc_blocks;                 /* 4 */
+  int32_t enc_in[SDXL_MAX_LEVELS];      /* 128, 128, 256, 512 */
+  int32_t enc_out[SDXL_MAX_LEVELS];     /* 128, 256, 512, 512 */
+  int32_t enc_z_channels;               /* 8 (mean + logvar); the first latent_channels are kept (autoencoder/mod.rs:62) */
 } sdxl_vae_cfg;
 
 /* replaces load_latent_decoder (stablediffusion/load.rs:70-84): same flat pack container as sdxl_unet_load. */
@@ -220,6 +225,15 @@ SDXL_API int sdxl_vae_decode_latent(sdxl_vae* vae, int B, int h, int w, const fl
 /* == LatentDecoder::latent_to_image (stablediffusion/mod.rs:200-237): RawImages buffer, u8 [B, 8h, 8w, 3],
  * value = trunc(clamp(((x + 1) / 2) * 255, 0, 255)). */
 SDXL_API int sdxl_vae_latent_to_image(sdxl_vae* vae, int B, int h, int w, const float* latent, int on_host, uint8_t* rgb_out);
+/* == LatentDecoder::encode_image (stablediffusion/mod.rs:258-261) over Autoencoder::encode_image (autoencoder/mod.rs:58-64):
+ * image f32 [B,3,H,W] NCHW in [-1,1] -> latent f32 [B,latent_channels,H/8,W/8] (mean channels of quant_conv, times
+ * scale_factor; no sampling, like the reference). Encoder weights: encoder/conv_in, encoder/blocks/<i>/{res1,res2,
+ * downsampler/conv}, encoder/mid/{block_1,attn,block_2}, encoder/norm_out, encoder/conv_out, quant_conv
+ * (autoencoder/load.rs:82-116). (H/8)*(W/8) must be a multiple of 64. */
+SDXL_API int sdxl_vae_encode_image(sdxl_vae* vae, int B, int H, int W, const float* image, int on_host, float* latent_out);
+/* == LatentDecoder::image_to_latent (stablediffusion/mod.rs:239-256): RawImages u8 [B,H,W,3] -> latent. */
+SDXL_API int sdxl_vae_image_to_latent(sdxl_vae* vae, int B, int H, int W, const uint8_t* rgb, int on_host, float* latent_out);
+SDXL_API double sdxl_vae_encode_plan_flops(const sdxl_vae* vae);
 /* algorithmic FLOPs (2*MAC over conv / linear / QK^T / PV) of the current decode plan; per-kind CUDA-event profile and
  * per-op CSV as for the UNet plan. */
 SDXL_API double sdxl_vae_plan_flops(const sdxl_vae* vae);

@@ -1,9 +1,9 @@
 """ORACLE — test infrastructure only. Never imported by the product path (sdxl_b200 / libsdxl_b200.so).
 
-CPU f32 restatement (PyTorch tensor ops) of the reference's latent decoder, written line-by-line from
-/root/reference (Gadersd/stable-diffusion-xl-burn): src/model/autoencoder/mod.rs (Autoencoder::decode_latent,
-Decoder, Mid, ResnetBlock, ConvSelfAttentionBlock, DecoderBlock) and src/model/stablediffusion/mod.rs:199-237,
-263-266 (LatentDecoder::{decode_latent, latent_to_image}).
+CPU f32 restatement (PyTorch tensor ops) of the reference's autoencoder, written line-by-line from
+/root/reference (Gadersd/stable-diffusion-xl-burn): src/model/autoencoder/mod.rs (Autoencoder::{decode_latent,
+encode_image}, Decoder, Encoder, Mid, ResnetBlock, ConvSelfAttentionBlock, DecoderBlock, EncoderBlock, PaddedConv2d) and
+src/model/stablediffusion/mod.rs:199-266 (LatentDecoder::{decode_latent, latent_to_image, encode_image, image_to_latent}).
 
     *** PARITY UNPINNED *** — the reference cannot be built here (no cargo/rustc, un-vendored burn/tch crates) and
     ships no numeric golden for the autoencoder; goldens under tests/golden/ come from THIS file
@@ -93,6 +93,74 @@ def latent_to_image(cfg, w: W, latent: torch.Tensor) -> torch.Tensor:
     image = (image + 1.0) / 2.0
     image = image.permute(0, 2, 3, 1) * 255.0
     return image.to(torch.float64).clamp(0.0, 255.0).to(torch.uint8)
+
+
+def padded_conv2d(x: torch.Tensor, w: W, p: str, kernel_size: int = 3, stride: int = 2, pad=(0, 1, 0, 1)) -> torch.Tensor:
+    """PaddedConv2d::{init, forward}, autoencoder/mod.rs:326-407 (pad = left, right, top, bottom): a symmetric conv with
+    padding calc_padding(..) followed by a slice that drops the leading outputs."""
+    pad_left, pad_right, pad_top, pad_bottom = pad
+
+    def calc_padding(p_left, p_right):
+        n = 0 if p_left >= p_right else (p_right - p_left + stride - 1) // stride
+        return n * stride + p_left
+    pv, ph = calc_padding(pad_top, pad_bottom), calc_padding(pad_left, pad_right)
+    n_batch, n_channel, height, width = x.shape
+    desired_h = (pad_top + pad_bottom + height - kernel_size) // stride + 1
+    desired_w = (pad_left + pad_right + width - kernel_size) // stride + 1
+    skip_v, skip_h = (pv - pad_top) // stride, (ph - pad_left) // stride
+    import torch.nn.functional as F
+    y = F.conv2d(x, w[f"{p}/conv/weight"], w.get(f"{p}/conv/bias"), stride=stride, padding=(pv, ph))
+    return y[:, :, skip_v:skip_v + desired_h, skip_h:skip_h + desired_w]
+
+
+def encoder_block(x: torch.Tensor, w: W, p: str) -> torch.Tensor:
+    """EncoderBlock::forward, autoencoder/mod.rs:284-295."""
+    x = resnet_block(x, w, f"{p}/res1")
+    x = resnet_block(x, w, f"{p}/res2")
+    if f"{p}/downsampler/conv/weight" in w:
+        x = padded_conv2d(x, w, f"{p}/downsampler")
+    return x
+
+
+def encoder_forward(cfg, w: W, x: torch.Tensor) -> torch.Tensor:
+    """Encoder::forward, autoencoder/mod.rs:128-144."""
+    x = conv2d(x, w, "encoder/conv_in")
+    for i in range(len(cfg.enc_block_channels)):
+        x = encoder_block(x, w, f"encoder/blocks/{i}")
+    x = mid(x, w, "encoder/mid")
+    x = silu(group_norm(x, w["encoder/norm_out/weight"], w["encoder/norm_out/bias"]))
+    return conv2d(x, w, "encoder/conv_out")
+
+
+def encode_image(cfg, w: W, image: torch.Tensor) -> torch.Tensor:
+    """LatentDecoder::encode_image (stablediffusion/mod.rs:258-261) over Autoencoder::encode_image (autoencoder/mod.rs:58-64):
+    quant_conv(encoder(x))[:, 0:4] * scale_factor (the mean channels; the reference does not sample)."""
+    latent = conv2d(encoder_forward(cfg, w, image), w, "quant_conv", padding=0)
+    return latent[:, 0:cfg.latent_channels] * cfg.scale_factor
+
+
+def image_to_latent(cfg, w: W, rgb_u8: torch.Tensor) -> torch.Tensor:
+    """LatentDecoder::image_to_latent (stablediffusion/mod.rs:239-256): u8 [B,H,W,3] / 255 -> NCHW -> * 2 - 1 -> encode."""
+    x = (rgb_u8.to(torch.float32) / 255.0).permute(0, 3, 1, 2) * 2.0 - 1.0
+    return encode_image(cfg, w, x)
+
+
+def encoder_flops(cfg, H: int, Wd: int, batch: int = 1) -> float:
+    """Algorithmic FLOPs of encode_image at image H x Wd (quant_conv counted on all z channels as the reference computes it)."""
+    c0, ce, cz = cfg.enc_block_channels[0][0], cfg.enc_block_channels[-1][1], cfg.enc_z_channels
+
+    def res(hw, ci, co):
+        return 2.0 * hw * 9 * (ci * co + co * co) + (2.0 * hw * ci * co if ci != co else 0.0)
+    hw = H * Wd
+    f = 2.0 * hw * 27 * c0
+    for i, (ci, co) in enumerate(cfg.enc_block_channels):
+        f += res(hw, ci, co) + res(hw, co, co)
+        if i != len(cfg.enc_block_channels) - 1:
+            hw //= 4
+            f += 2.0 * hw * 9 * co * co
+    f += 2 * res(hw, ce, ce) + 4 * 2.0 * hw * ce * ce + 2 * 2.0 * hw * hw * ce
+    f += 2.0 * hw * 9 * ce * cz + 2.0 * hw * cz * cz
+    return f * batch
 
 
 def decoder_flops(cfg, h: int, wd: int, batch: int = 1) -> float:

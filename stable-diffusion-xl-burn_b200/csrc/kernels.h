@@ -205,6 +205,12 @@ int post_quant_launch(cudaStream_t st, const float* x, int B, int C, int HW, con
 // u8[b,p,c] = trunc(clamp(((x+1)/2)*255, 0, 255)), c < 3, from NHWC f32 [npix, ldx].
 int image_u8_launch(cudaStream_t st, const float* x, long npix, int ldx, uint8_t* out);
 
+// u8 [B,HW,3] -> f32 NCHW [B,3,HW], ((v/255)*2)-1.
+int image_from_u8_launch(cudaStream_t st, const uint8_t* in, int B, long HW, float* out);
+// quant_conv on the first Cout output channels, times scale: x NHWC f32 [B,HW,Cz] -> y NCHW f32 [B,Cout,HW]; w f32 [Cz,Cz].
+int quant_out_launch(cudaStream_t st, const float* x, int B, int Cz, int Cout, long HW, const float* w, const float* bias,
+                     float scale, float* y);
+
 // Text-encoder kernels (clip_kernels.cu)
 // x[b*T+t,:] = tok_emb[tokens[b,t],:] + pos_emb[t,:] (f16 tables -> f32); *err is set to 1 on an id outside [0, n_vocab).
 int embed_tokens_launch(cudaStream_t st, const int* tokens, int rows, int T, int C, int n_vocab, const __half* tok_emb,

@@ -174,4 +174,52 @@ int image_u8_launch(cudaStream_t st, const float* x, long npix, int ldx, uint8_t
   return (int)cudaGetLastError();
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// image_to_latent front end (reference stablediffusion/mod.rs:239-256): u8 [B, HW, 3] -> f32 NCHW [B, 3, HW],
+// ((v / 255) * 2) - 1 in f32, in that order.
+// ------------------------------------------------------------------------------------------------
+__global__ void image_from_u8_kernel(const uint8_t* __restrict__ in, int B, long HW, float* __restrict__ out) {
+  const long total = (long)B * HW;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long b = i / HW, p = i % HW;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[((size_t)b * 3 + c) * HW + p] = ((float)in[(size_t)i * 3 + c] / 255.0f) * 2.0f - 1.0f;
+  }
+}
+int image_from_u8_launch(cudaStream_t st, const uint8_t* in, int B, long HW, float* out) {
+  int grid = cdiv((long)B * HW, 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  image_from_u8_kernel<<<grid, 256, 0, st>>>(in, B, HW, out);
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// quant_conv + slice + scale (reference autoencoder/mod.rs:58-64, stablediffusion/mod.rs:258-261):
+// y[b, o, p] = (bias[o] + sum_i w[o, i] * x[b, p, i]) * scale for o < Cout (the first Cout of the Cz moments channels);
+// x NHWC f32 [B, HW, Cz], y NCHW f32 [B, Cout, HW]. Exact f32.
+// ------------------------------------------------------------------------------------------------
+__global__ void quant_out_kernel(const float* __restrict__ x, int B, int Cz, int Cout, long HW, const float* __restrict__ w,
+                                 const float* __restrict__ bias, float scale, float* __restrict__ y) {
+  const long total = (long)B * HW;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long b = i / HW, p = i % HW;
+    float v[16];
+    for (int c = 0; c < Cz; ++c) v[c] = x[(size_t)i * Cz + c];
+    for (int o = 0; o < Cout; ++o) {
+      float acc = 0.f;
+      for (int c = 0; c < Cz; ++c) acc = fmaf(w[o * Cz + c], v[c], acc);
+      y[((size_t)b * Cout + o) * HW + p] = (acc + bias[o]) * scale;
+    }
+  }
+}
+int quant_out_launch(cudaStream_t st, const float* x, int B, int Cz, int Cout, long HW, const float* w, const float* bias,
+                     float scale, float* y) {
+  if (Cz > 16 || Cout > Cz || Cout < 1) return 6004;
+  int grid = cdiv((long)B * HW, 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  quant_out_kernel<<<grid, 256, 0, st>>>(x, B, Cz, Cout, HW, w, bias, scale, y);
+  return (int)cudaGetLastError();
+}
+
 }  // namespace sdxl

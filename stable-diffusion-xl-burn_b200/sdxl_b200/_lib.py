@@ -47,6 +47,8 @@ class VaeCfg(C.Structure):
         ("latent_channels", C.c_int32), ("n_blocks", C.c_int32),
         ("block_in", C.c_int32 * SDXL_MAX_LEVELS), ("block_out", C.c_int32 * SDXL_MAX_LEVELS),
         ("n_group", C.c_int32), ("scale_factor", C.c_double),
+        ("n_enc_blocks", C.c_int32), ("enc_in", C.c_int32 * SDXL_MAX_LEVELS), ("enc_out", C.c_int32 * SDXL_MAX_LEVELS),
+        ("enc_z_channels", C.c_int32),
     ]
 
 
@@ -91,6 +93,9 @@ PROTOTYPES = {
     "sdxl_vae_destroy": (None, [P]),
     "sdxl_vae_decode_latent": (I, [P, I, I, I, P, I, P]),
     "sdxl_vae_latent_to_image": (I, [P, I, I, I, P, I, P]),
+    "sdxl_vae_encode_image": (I, [P, I, I, I, P, I, P]),
+    "sdxl_vae_image_to_latent": (I, [P, I, I, I, P, I, P]),
+    "sdxl_vae_encode_plan_flops": (C.c_double, [P]),
     "sdxl_vae_plan_flops": (C.c_double, [P]),
     "sdxl_vae_profile_plan": (I, [P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "sdxl_vae_profile_dump": (I, [P, C.c_char_p]),

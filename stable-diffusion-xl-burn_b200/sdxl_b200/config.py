@@ -54,6 +54,8 @@ class VaeConfig:
     latent_channels: int = 4
     n_group: int = 32
     scale_factor: float = 0.13025
+    enc_block_channels: Tuple[Tuple[int, int], ...] = ()   # EncoderConfig channels; () = decoder only
+    enc_z_channels: int = 8
 
     @property
     def upscale(self) -> int:
@@ -61,9 +63,11 @@ class VaeConfig:
 
 
 # SDXL VAE decoder: DecoderConfig::new(vec![(512,512),(512,512),(512,256),(256,128)], 32)
-SDXL_VAE = VaeConfig(block_channels=((512, 512), (512, 512), (512, 256), (256, 128)))
+# and EncoderConfig::new(vec![(128,128),(128,256),(256,512),(512,512)], 32, 8)
+SDXL_VAE = VaeConfig(block_channels=((512, 512), (512, 512), (512, 256), (256, 128)),
+                     enc_block_channels=((128, 128), (128, 256), (256, 512), (512, 512)))
 # small instance with the same topology rules (3 ResnetBlocks per level, nin_shortcut where widths change)
-TINY_VAE = VaeConfig(block_channels=((128, 128), (128, 64), (64, 64)))
+TINY_VAE = VaeConfig(block_channels=((128, 128), (128, 64), (64, 64)), enc_block_channels=((64, 64), (64, 128), (128, 128)))
 
 
 @dataclass(frozen=True)

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from .config import ClipConfig, UNetConfig, VaeConfig
-from .weights import build_pack, clip_tensor_specs, unet_tensor_specs, vae_decoder_tensor_specs
+from .weights import build_pack, clip_tensor_specs, unet_tensor_specs, vae_tensor_specs
 
 
 class NpyTreeError(RuntimeError):
@@ -55,7 +55,7 @@ def _specs(cfg) -> Iterable[Tuple[str, Tuple[int, ...]]]:
     if isinstance(cfg, UNetConfig):
         return [(s[0], s[1]) for s in unet_tensor_specs(cfg)]
     if isinstance(cfg, VaeConfig):
-        return [(s[0], s[1]) for s in vae_decoder_tensor_specs(cfg)]
+        return [(s[0], s[1]) for s in vae_tensor_specs(cfg)]
     if isinstance(cfg, ClipConfig):
         return [(s[0], s[1]) for s in clip_tensor_specs(cfg)]
     raise TypeError(f"unsupported config {type(cfg).__name__}")

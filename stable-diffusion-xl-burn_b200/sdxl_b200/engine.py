@@ -410,6 +410,9 @@ class LatentDecoder:
         cs.scale_factor = cfg.scale_factor
         for i, (ci, co) in enumerate(cfg.block_channels):
             cs.block_in[i], cs.block_out[i] = ci, co
+        cs.n_enc_blocks, cs.enc_z_channels = len(cfg.enc_block_channels), cfg.enc_z_channels
+        for i, (ci, co) in enumerate(cfg.enc_block_channels):
+            cs.enc_in[i], cs.enc_out[i] = ci, co
         h = C.c_void_p()
         ctx.check(ctx.lib.sdxl_vae_load(ctx.h, C.byref(cs), pack.data_ptr(), pack.numel(), int(on_device), C.byref(h)),
                   "sdxl_vae_load")
@@ -452,6 +455,34 @@ class LatentDecoder:
                        "sdxl_vae_latent_to_image")
         self.ctx.leave()
         return out
+
+    def encode_image(self, image: torch.Tensor) -> torch.Tensor:
+        """== LatentDecoder::encode_image: image f32 [B,3,H,W] in [-1,1] (host or device) -> latent f32 [B,4,H/8,W/8]."""
+        host = not image.is_cuda
+        image = image.to(torch.float32).contiguous()
+        B, _, H, W = image.shape
+        d = 2 ** (len(self.cfg.enc_block_channels) - 1)
+        out = torch.empty((B, self.cfg.latent_channels, H // d, W // d), dtype=torch.float32, device="cpu" if host else self.ctx.device)
+        self.ctx.enter()
+        self.ctx.check(self.ctx.lib.sdxl_vae_encode_image(self.h, B, H, W, _ptr(image), int(host), _ptr(out)), "sdxl_vae_encode_image")
+        self.ctx.leave()
+        return out
+
+    def image_to_latent(self, rgb: torch.Tensor) -> torch.Tensor:
+        """== LatentDecoder::image_to_latent: RawImages u8 [B,H,W,3] -> latent f32 [B,4,H/8,W/8]."""
+        host = not rgb.is_cuda
+        rgb = rgb.to(torch.uint8).contiguous()
+        B, H, W, _ = rgb.shape
+        d = 2 ** (len(self.cfg.enc_block_channels) - 1)
+        out = torch.empty((B, self.cfg.latent_channels, H // d, W // d), dtype=torch.float32, device="cpu" if host else self.ctx.device)
+        self.ctx.enter()
+        self.ctx.check(self.ctx.lib.sdxl_vae_image_to_latent(self.h, B, H, W, _ptr(rgb), int(host), _ptr(out)), "sdxl_vae_image_to_latent")
+        self.ctx.leave()
+        return out
+
+    @property
+    def encode_plan_flops(self) -> float:
+        return float(self.ctx.lib.sdxl_vae_encode_plan_flops(self.h))
 
     @property
     def plan_flops(self) -> float:

@@ -110,6 +110,33 @@ def _vres_specs(path: str, c_in: int, c_out: int) -> List[Spec]:
     return s
 
 
+def vae_encoder_tensor_specs(cfg: VaeConfig) -> List[Spec]:
+    """Encoder-side tensors of the autoencoder dump tree (reference src/model/autoencoder/load.rs:38-51, 80-116)."""
+    if not cfg.enc_block_channels:
+        return []
+    c0, ce, cz = cfg.enc_block_channels[0][0], cfg.enc_block_channels[-1][1], cfg.enc_z_channels
+    s: List[Spec] = [("encoder/conv_in/weight", (c0, 3, 3, 3), "conv", 1.0), ("encoder/conv_in/bias", (c0,), "bias", 1.0)]
+    for i, (ci, co) in enumerate(cfg.enc_block_channels):
+        b = f"encoder/blocks/{i}"
+        s += _vres_specs(f"{b}/res1", ci, co) + _vres_specs(f"{b}/res2", co, co)
+        if i != len(cfg.enc_block_channels) - 1:
+            s += [(f"{b}/downsampler/conv/weight", (co, co, 3, 3), "conv", 1.0), (f"{b}/downsampler/conv/bias", (co,), "bias", 1.0)]
+    s += _vres_specs("encoder/mid/block_1", ce, ce)
+    s += [("encoder/mid/attn/norm/weight", (ce,), "gamma", 1.0), ("encoder/mid/attn/norm/bias", (ce,), "beta", 1.0)]
+    for n, sc in (("q", 1.0), ("k", 1.0), ("v", 1.0), ("proj_out", RESID_SCALE)):
+        s += [(f"encoder/mid/attn/{n}/weight", (ce, ce, 1, 1), "conv", sc), (f"encoder/mid/attn/{n}/bias", (ce,), "bias", 1.0)]
+    s += _vres_specs("encoder/mid/block_2", ce, ce)
+    s += [("encoder/norm_out/weight", (ce,), "gamma", 1.0), ("encoder/norm_out/bias", (ce,), "beta", 1.0),
+          ("encoder/conv_out/weight", (cz, ce, 3, 3), "conv", 1.0), ("encoder/conv_out/bias", (cz,), "bias", 1.0),
+          ("quant_conv/weight", (cz, cz, 1, 1), "conv", 1.0), ("quant_conv/bias", (cz,), "bias", 1.0)]
+    return s
+
+
+def vae_tensor_specs(cfg: VaeConfig) -> List[Spec]:
+    """Decoder tensors first (so seeded synthetic decoder weights do not depend on the encoder), then the encoder's."""
+    return vae_decoder_tensor_specs(cfg) + vae_encoder_tensor_specs(cfg)
+
+
 def vae_decoder_tensor_specs(cfg: VaeConfig) -> List[Spec]:
     """Decoder-side tensors of the autoencoder dump tree (reference src/model/autoencoder/load.rs:17-76, 107-114)."""
     cl, c0 = cfg.latent_channels, cfg.block_channels[0][0]
@@ -165,7 +192,7 @@ def synth_weights(cfg, seed: int = 0, device: str = "cpu") -> Dict[str, torch.Te
     out: Dict[str, torch.Tensor] = {}
     is_vae = isinstance(cfg, VaeConfig)
     is_clip = isinstance(cfg, ClipConfig)
-    specs = vae_decoder_tensor_specs(cfg) if is_vae else clip_tensor_specs(cfg) if is_clip else unet_tensor_specs(cfg)
+    specs = vae_tensor_specs(cfg) if is_vae else clip_tensor_specs(cfg) if is_clip else unet_tensor_specs(cfg)
     for name, shape, kind, scale in specs:
         if kind == "linear":
             t = torch.randn(shape, generator=gen, device=device) * (scale / shape[0] ** 0.5)

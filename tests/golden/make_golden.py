@@ -43,6 +43,11 @@ def vae():
     u8 = VO.latent_to_image(TINY_VAE, w, latent)
     np.savez(os.path.join(HERE, "tiny_vae_decode.npz"), latent=latent.numpy(), image=img.numpy(), u8=u8.numpy())
     print("tiny_vae_decode", img.shape, float(img.abs().mean()), float(u8.float().mean()))
+    # encoder half: u8 image (a deterministic pattern) -> latent
+    rgb = ((arb(1, 64, 96, 3) * 0.5 + 0.5) * 255.0).to(torch.uint8)
+    lat = VO.image_to_latent(TINY_VAE, w, rgb)
+    np.savez(os.path.join(HERE, "tiny_vae_encode.npz"), rgb=rgb.numpy(), latent=lat.numpy())
+    print("tiny_vae_encode", lat.shape, float(lat.abs().mean()))
 
 
 def clip():

@@ -64,3 +64,36 @@ def test_vae_golden_reproduces():
     w = O.to_f32(synth_weights(TINY_VAE, seed=0))
     img = VO.decode_latent(TINY_VAE, w, torch.from_numpy(g["latent"]))
     assert np.allclose(img.numpy(), g["image"], atol=2e-5, rtol=1e-5)
+
+
+def test_encoder_flops_match_survey():
+    assert abs(VO.encoder_flops(SDXL_VAE, 1024, 1024) / 1e12 - 4.88) < 0.01
+
+
+def test_padded_conv_is_bottom_right_padding():
+    """PaddedConv2d(3, stride 2, pad (0,1,0,1)) == zero-pad one row/column at the bottom/right, then a valid stride-2 conv."""
+    w = O.to_f32(synth_weights(TINY_VAE, seed=0))
+    p = "encoder/blocks/0/downsampler"
+    for hw in ((10, 12), (8, 8), (6, 14)):
+        x = torch.randn(2, 64, *hw, generator=torch.Generator().manual_seed(hw[0]))
+        want = F.conv2d(F.pad(x, (0, 1, 0, 1)), w[f"{p}/conv/weight"], w[f"{p}/conv/bias"], stride=2)
+        got = VO.padded_conv2d(x, w, p)
+        assert got.shape == want.shape == (2, 64, hw[0] // 2, hw[1] // 2) and torch.allclose(got, want, atol=1e-6)
+
+
+def test_encode_keeps_mean_channels_and_scales():
+    w = O.to_f32(synth_weights(TINY_VAE, seed=0))
+    x = torch.randn(1, 3, 64, 64, generator=torch.Generator().manual_seed(4))
+    z = F.conv2d(VO.encoder_forward(TINY_VAE, w, x), w["quant_conv/weight"], w["quant_conv/bias"])
+    assert z.shape == (1, 8, 16, 16)
+    assert torch.allclose(VO.encode_image(TINY_VAE, w, x), z[:, :4] * TINY_VAE.scale_factor)
+    rgb = torch.randint(0, 256, (1, 64, 64, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(5))
+    want = VO.encode_image(TINY_VAE, w, (rgb.float() / 255.0).permute(0, 3, 1, 2) * 2.0 - 1.0)
+    assert torch.equal(VO.image_to_latent(TINY_VAE, w, rgb), want)
+
+
+def test_vae_encode_golden_reproduces():
+    g = np.load(os.path.join(GOLD, "tiny_vae_encode.npz"))
+    w = O.to_f32(synth_weights(TINY_VAE, seed=0))
+    lat = VO.image_to_latent(TINY_VAE, w, torch.from_numpy(g["rgb"]))
+    assert np.allclose(lat.numpy(), g["latent"], atol=2e-5, rtol=1e-5)
