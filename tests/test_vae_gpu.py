@@ -162,6 +162,6 @@ def test_sdxl_vae_encode_1024_properties(full):
     assert torch.equal(a, d.image_to_latent(rgb))                                       # deterministic
     img = (rgb.float() / 255.0).permute(0, 3, 1, 2) * 2.0 - 1.0
     # u8 front end == f32 entry point, up to torch's own CUDA `x / 255` (multiplies by the reciprocal: 1 ulp off true division)
-    assert rel_err(a, d.encode_image(img.contiguous())) <= 2e-4
+    assert rel_err(a, d.encode_image(img.contiguous())) <= TOL      # 1-ulp input changes flip f16 operand roundings: same noise floor
     # encode -> decode round trip runs and stays finite (synthetic weights: no reconstruction claim)
     assert torch.isfinite(d.decode_latent(a)).all()
