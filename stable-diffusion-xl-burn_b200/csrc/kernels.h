@@ -88,6 +88,9 @@ struct alignas(64) IgemmParams {
   int bias_bstride;
   const float* res;           // nullable f32 residual [pixels, ldr]
   int ldr;
+  // host-computed reciprocals (floor(2^32/d)+1; q = umulhi(n, m), exact while n*d < 2^32; 0 = use '/') for the tile-index
+  // divisions of the producer warp: on the critical path between griddepcontrol.wait and the first TMA issue
+  unsigned fd_pm, fd_w, fd_h, fd_wh;   // divisors: pair M tiles (or M tiles), tilesW, tilesH, tilesW*tilesH
   int dbg_mode;               // diagnostics only: 1 = skip TMA loads, 2 = skip MMAs (results are garbage)
   unsigned long long* dbg;    // nullable: per-role %globaltimer stamps of CTA 0 (tools/igemm_timeline.py)
 };

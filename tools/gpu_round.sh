@@ -7,6 +7,8 @@ echo "== pytest: $(tail -1 gpurun_out/pytest_gpu_$R.log)"
 timeout 900 python bench.py > gpurun_out/bench_$R.json 2> gpurun_out/bench_$R.err
 echo "== bench: $(head -c 600 gpurun_out/bench_$R.json)"
 tail -5 gpurun_out/bench_$R.err
+timeout 300 python tools/vae_bench.py 1 gpurun_out/ops_vae_$R.csv > gpurun_out/vae_bench_$R.json 2>/dev/null
+echo "== vae: $(cat gpurun_out/vae_bench_$R.json)"
 if [ "$2" != "noncu" ]; then
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --nvtx --nvtx-include "timed/" --csv \
   --log-file gpurun_out/launches_$R.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench_$R.log 2>&1
