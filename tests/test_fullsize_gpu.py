@@ -67,3 +67,44 @@ def test_base_1024_properties(base):
     # every kernel sums each sample in an order that does not depend on the batch size (tile shapes only change
     # which CTA owns an output), so the CFG-batched forward is bit-identical to the reference's two bs=1 forwards
     assert torch.equal(a, out2[:1]) and torch.equal(b, out2[1:])
+
+
+def test_base_1024_inpaint_sampler_runs(base):
+    """BASELINE config 5 shape (1024^2 inpainting, mask = top 25 latent rows): a short seeded run is finite, deterministic,
+    and leaves exactly the unmasked region driven by the re-noised reference at the last step."""
+    from sdxl_b200 import Conditioning
+    d, _ = base
+    g = torch.Generator().manual_seed(5)
+    c = Conditioning(context_full=torch.randn(1, 77, 2048, generator=g).half(), unconditional_context_full=torch.randn(77, 2048, generator=g).half(),
+                     channel_context=torch.randn(1, 2816, generator=g).half(), unconditional_channel_context=torch.randn(2816, generator=g).half(),
+                     resolution=(1024, 1024))
+    ref = torch.randn(1, 4, 128, 128, generator=g)
+    mask = torch.zeros(1, 4, 128, 128, dtype=torch.bool)
+    mask[:, :, :25] = True
+    a = d.sample_latent_with_inpainting(c, 7.5, 3, ref, mask, seed=11)
+    b = d.sample_latent_with_inpainting(c, 7.5, 3, ref, mask, seed=11)
+    assert a.shape == (1, 4, 128, 128) and torch.isfinite(a).all() and torch.equal(a, b)
+    assert not torch.equal(a, d.sample_latent_with_inpainting(c, 7.5, 3, ref, mask, seed=12))
+
+
+def test_refiner_1024_properties(ctx):
+    """SDXL refiner (384 / [1,2,4,4] / depth 4, 2.26 B parameters; BASELINE config 4): plan FLOPs against SURVEY 8(d)
+    (7.2860 TFLOP per forward at 1024^2), determinism, and one refine_latent run (step_start 800, n=50 -> 10 iterations, no CFG)."""
+    from sdxl_b200 import SDXL_REFINER, Conditioning
+    w = sdxl_b200.synth_weights(SDXL_REFINER, seed=2, device=str(ctx.device))
+    d = Diffuser(ctx, SDXL_REFINER, sdxl_b200.build_pack(w))
+    del w
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(1, 4, 128, 128, generator=g)
+    ctx_t = torch.randn(1, 77, 1280, generator=g).half()
+    y = torch.randn(1, 2560, generator=g).half()
+    out = d.unet_forward(x, [199], ctx_t.float(), y.float())
+    assert torch.isfinite(out).all() and out.shape == (1, 4, 128, 128)
+    print(f"refiner plan FLOPs 1024^2: {d.plan_flops:.6e}")
+    assert abs(d.plan_flops / 7.2860e12 - 1) < 2e-4
+    assert torch.equal(out, d.unet_forward(x, [199]))
+    c = Conditioning(context_open_clip=ctx_t, channel_context_refiner=y, unconditional_context_open_clip=ctx_t[0], unconditional_channel_context_refiner=y[0],
+                     resolution=(1024, 1024))
+    lat = d.refine_latent(x, c, 7.5, 800, 50, seed=4)
+    assert lat.shape == (1, 4, 128, 128) and torch.isfinite(lat).all()
+    d.close()
