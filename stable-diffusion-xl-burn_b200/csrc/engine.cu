@@ -180,6 +180,17 @@ static STrans load_st(Loader& L, const std::string& path, int C, int ctx_dim, in
     if (!gbn) { L.err = fail(L.c, 4009, "GEGLU width %d not tileable", 4 * C); break; }
     b.ff1 = L.linear(bp + "/mlp/geglu/proj", C, 8 * C, true, gbn);
     b.ff2 = L.linear(bp + "/mlp/lin", 4 * C, C, true);
+    // LayerNorm fold (EXPERIMENTAL, off by default: SDXL_B200_LN_FOLD=1): norm1 -> qkv, norm2 -> attn2/query, norm3 -> GEGLU
+    // projection (each LayerNorm has exactly one consumer, unet/mod.rs:885-891). Parity holds (tests/test_unet_gpu.py runs it in a
+    // subprocess) but the first implementation is slower than the separate LayerNorm passes (22.5 vs 21.0 ms per step: the
+    // consumer epilogue's u/v loads serialise and spill at the 168-register ceiling, +15 us on the qkv GEMM) and it gives up
+    // bit-exact batch invariance (tile-dependent partial-sum order); see profiles/README.md.
+    static const bool fold = getenv("SDXL_B200_LN_FOLD") != nullptr && atoi(getenv("SDXL_B200_LN_FOLD")) != 0;
+    if (fold) {
+      L.fold_ln(b.qkv, b.n1);
+      L.fold_ln(b.q2, b.n2);
+      L.fold_ln(b.ff1, b.n3);
+    }
     s.blocks.push_back(b);
   }
   return s;
@@ -421,12 +432,37 @@ struct UNetPlanBuilder : PlanBuilder {
 
   // ---- SpatialTransformer (reference unet/mod.rs:820-845, 885-891, 1005-1023) ----
   float* strans(const STrans& s, const float* x, int H, int W, __half* s_a16, float* s_tok, __half* s_qkv, __half* s_ao,
-                __half* s_q, __half* s_ff) {
+                __half* s_q, __half* s_ff, __half* s_x16, float2* s_stats) {
     const int T = H * W, M = Bf * T, C = s.C;
     float* out = buf<float>((size_t)M * C);
-    gn(x, C, nullptr, 0, T, s.norm, 0, s_a16, nullptr);
-    linear(s_a16, M, s.proj_in, IGEMM_LINEAR, s_tok, 1, C, nullptr, 0);
+    const bool fold = !s.blocks.empty() && s.blocks[0].qkv.ln_u != nullptr;
     const float sl2e = (float)(1.4426950408889634 / sqrt(64.0));
+    gn(x, C, nullptr, 0, T, s.norm, 0, s_a16, nullptr);
+    if (fold) {
+      // Every LayerNorm is folded into the GEMMs around it: the residual GEMMs ("producers") emit the f16 copy of the token
+      // stream plus per-row partial statistics, the Linear after the LayerNorm ("consumer") normalises in its epilogue.
+      int slots = linear_ln_producer(s_a16, M, s.proj_in, s_tok, C, nullptr, s_x16, s_stats);
+      for (const TBlock& b : s.blocks) {
+        // x = x + attn1(norm1(x))
+        linear_ln_consumer(s_x16, M, b.qkv, IGEMM_LINEAR, s_qkv, 3 * C, s_stats, slots);
+        attn(s_qkv, 3 * C, 0, s_qkv, 3 * C, C, 2 * C, T, T, s.n_head, s_ao, C, sl2e);
+        slots = linear_ln_producer(s_ao, M, b.out1, s_tok, C, s_tok, s_x16, s_stats);
+        // x = x + attn2(norm2(x), context)   (K/V hoisted to set_conditioning)
+        linear_ln_consumer(s_x16, M, b.q2, IGEMM_LINEAR, s_q, C, s_stats, slots);
+        const __half* kvp = A->measure ? nullptr : u->kv[kv_index];
+        attn(s_q, C, 0, kvp, 2 * C, 0, C, T, u->n_ctx, s.n_head, s_ao, C, sl2e);
+        P->flops += 2.0 * Bf * u->n_ctx * (double)b.kv2.K * b.kv2.N;  // hoisted K/V projections (algorithmic work)
+        kv_index++;
+        slots = linear_ln_producer(s_ao, M, b.out2, s_tok, C, s_tok, s_x16, s_stats);
+        // x = x + mlp(norm3(x))
+        linear_ln_consumer(s_x16, M, b.ff1, IGEMM_GEGLU, s_ff, 4 * C, s_stats, slots);
+        slots = linear_ln_producer(s_ff, M, b.ff2, s_tok, C, s_tok, s_x16, s_stats);
+      }
+      // proj_out(tokens) + x_in: the last producer's f16 copy is the operand
+      linear(s_x16, M, s.proj_out, IGEMM_LINEAR, out, 1, C, x, C);
+      return out;
+    }
+    linear(s_a16, M, s.proj_in, IGEMM_LINEAR, s_tok, 1, C, nullptr, 0);
     for (const TBlock& b : s.blocks) {
       // x = x + attn1(norm1(x))
       ln(s_tok, b.n1, M, s_a16);
@@ -500,7 +536,7 @@ static int build_plan_ops(sdxl_unet* u, Plan* P, Arena* A) {
   float* temb_all = B.buf<float>((size_t)Bf * temb_total);
 
   // maxima for the shared scratch buffers
-  size_t max_pixC_cat = 0, max_pixC = 0, max_tokC = 0;
+  size_t max_pixC_cat = 0, max_pixC = 0, max_tokC = 0, max_tok = 0;
   {
     int H = P->h, W = P->w;
     auto upd = [&](const Res& r, int hh, int ww) {
@@ -509,15 +545,16 @@ static int build_plan_ops(sdxl_unet* u, Plan* P, Arena* A) {
     };
     for (auto& b : u->in_blocks) {
       if (b.type == BT_RES || b.type == BT_REST) upd(b.res, H, W);
-      if (b.type == BT_REST) max_tokC = std::max(max_tokC, (size_t)H * W * b.st.C);
+      if (b.type == BT_REST) { max_tokC = std::max(max_tokC, (size_t)H * W * b.st.C); max_tok = std::max(max_tok, (size_t)H * W); }
       if (b.type == BT_DOWN) { H /= 2; W /= 2; }
     }
     upd(u->mid_res1, H, W);
     upd(u->mid_res2, H, W);
     max_tokC = std::max(max_tokC, (size_t)H * W * u->mid_st.C);
+    max_tok = std::max(max_tok, (size_t)H * W);
     for (auto& b : u->out_blocks) {
       upd(b.res, H, W);
-      if (b.type == BT_REST || b.type == BT_RESTU) max_tokC = std::max(max_tokC, (size_t)H * W * b.st.C);
+      if (b.type == BT_REST || b.type == BT_RESTU) { max_tokC = std::max(max_tokC, (size_t)H * W * b.st.C); max_tok = std::max(max_tok, (size_t)H * W); }
       if (b.type == BT_RESTU || b.type == BT_RESU) { H *= 2; W *= 2; }
     }
   }
@@ -531,6 +568,8 @@ static int build_plan_ops(sdxl_unet* u, Plan* P, Arena* A) {
   __half* s_ao = B.buf<__half>(Bf * max_tokC);
   __half* s_q = B.buf<__half>(Bf * max_tokC);
   __half* s_ff = B.buf<__half>(Bf * max_tokC * 4);
+  __half* s_x16 = B.buf<__half>(Bf * max_tokC);                       // LayerNorm fold: f16 copy of the token stream
+  float2* s_stats = B.buf<float2>((size_t)PlanBuilder::kMaxLnSlots * Bf * max_tok);  // ... and per-row partial (sum, sum sq)
   if (B.err) return B.err;
 
   // --- embeddings (unet/mod.rs:458-468): emb = time_mlp(temb(t)) + label_emb; only SiLU(emb) is consumed
@@ -563,7 +602,7 @@ static int build_plan_ops(sdxl_unet* u, Plan* P, Arena* A) {
     if (b.type == BT_RES || b.type == BT_REST) {
       x = B.resblock(b.res, x, Cx, nullptr, 0, H, W, temb_all, temb_total, s_gn1, s_raw, s_h, s_gn2);
       Cx = b.res.Cout;
-      if (b.type == BT_REST) x = B.strans(b.st, x, H, W, s_a16, s_tok, s_qkv, s_ao, s_q, s_ff);
+      if (b.type == BT_REST) x = B.strans(b.st, x, H, W, s_a16, s_tok, s_qkv, s_ao, s_q, s_ff, s_x16, s_stats);
     } else if (b.type == BT_DOWN) {
       // 3x3 stride 2 pad 1 (unet/mod.rs:760-774) on phase-split input: tap kh -> (phase, offset)
       __half* ph = B.buf<__half>((size_t)Bf * H * W * Cx);
@@ -589,7 +628,7 @@ static int build_plan_ops(sdxl_unet* u, Plan* P, Arena* A) {
   }
   // --- middle
   x = B.resblock(u->mid_res1, x, Cx, nullptr, 0, H, W, temb_all, temb_total, s_gn1, s_raw, s_h, s_gn2);
-  x = B.strans(u->mid_st, x, H, W, s_a16, s_tok, s_qkv, s_ao, s_q, s_ff);
+  x = B.strans(u->mid_st, x, H, W, s_a16, s_tok, s_qkv, s_ao, s_q, s_ff, s_x16, s_stats);
   x = B.resblock(u->mid_res2, x, Cx, nullptr, 0, H, W, temb_all, temb_total, s_gn1, s_raw, s_h, s_gn2);
   // --- output blocks: cat([x, saved.pop()], channel) is never materialised (GN + skip conv read both)
   for (size_t i = 0; i < u->out_blocks.size() && !B.err; ++i) {
@@ -600,7 +639,7 @@ static int build_plan_ops(sdxl_unet* u, Plan* P, Arena* A) {
     if (sk.H != H || sk.W != W || Cx + sk.C != b.res.Cin) return fail(c, 5005, "skip shape mismatch at output block %zu", i);
     x = B.resblock(b.res, x, Cx, sk.p, sk.C, H, W, temb_all, temb_total, s_gn1, s_raw, s_h, s_gn2);
     Cx = b.res.Cout;
-    if (b.type == BT_REST || b.type == BT_RESTU) x = B.strans(b.st, x, H, W, s_a16, s_tok, s_qkv, s_ao, s_q, s_ff);
+    if (b.type == BT_REST || b.type == BT_RESTU) x = B.strans(b.st, x, H, W, s_a16, s_tok, s_qkv, s_ao, s_q, s_ff, s_x16, s_stats);
     if (b.type == BT_RESTU || b.type == BT_RESU) {
       // nearest-2x then 3x3 conv (unet/mod.rs:742-751)
       __half* up = B.buf<__half>((size_t)Bf * 4 * H * W * Cx);

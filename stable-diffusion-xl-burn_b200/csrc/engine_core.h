@@ -115,7 +115,11 @@ struct PackView {
 // ================================================================================================
 // layer records + loader
 // ================================================================================================
-struct Lin { __half* w = nullptr; float* b = nullptr; int K = 0, Kpad = 0, N = 0, geglu_bn = 0; };
+struct Lin {
+  __half* w = nullptr; float* b = nullptr; int K = 0, Kpad = 0, N = 0, geglu_bn = 0;
+  // set when the preceding LayerNorm was folded into this layer at load time (IgemmParams::ln_mode 2): w holds gamma*W
+  float* ln_u = nullptr; float* ln_v = nullptr; float ln_eps = 0.f;
+};
 struct Conv { __half* w = nullptr; float* b = nullptr; int I = 0, O = 0, ks = 0, Ipad = 0, I2 = 0, I2pad = 0, Ktot = 0; };
 struct Norm { float* g = nullptr; float* b = nullptr; int C = 0; float eps = 1e-5f; };
 
@@ -165,6 +169,15 @@ struct Loader {
     if (lin_into(path, L.w, L.Kpad, 0, K, N, geglu_bn)) return L;
     if (bias) L.b = vec_f32(path + "/bias", N, geglu_bn);
     return L;
+  }
+  // Folds LayerNorm `n` into the Linear that consumes its output (elementwise.cu: ln_fold_kernel); L.b is absorbed into ln_v.
+  void fold_ln(Lin& L, const Norm& n) {
+    if (err) return;
+    L.ln_u = A->get<float>(L.N);
+    L.ln_v = A->get<float>(L.N);
+    L.ln_eps = n.eps;
+    if (!L.ln_u || !L.ln_v) { err = fail(c, 4005, "weight arena exhausted"); return; }
+    if (!A->measure) { int r = ln_fold_launch(st, L.w, L.N, L.K, L.Kpad, n.g, n.b, L.b, L.ln_u, L.ln_v); if (r) err = fail(c, r, "ln_fold failed"); }
   }
   Norm norm(const std::string& path, int C) {
     Norm n;
@@ -345,6 +358,29 @@ struct PlanBuilder {
     std::vector<IgemmSeg> segs{{0, 0, 0, 0, L.Kpad / 64}};
     igemm(a, nullptr, segs, L.w, L.N, L.Kpad, 1, M, 1, mode, L.geglu_bn, out, out_f32, ldo, L.b, 0, res, ldr);
     add_flops(2.0 * M * (double)L.K * L.N);
+  }
+  // LayerNorm fold (kernels.h: IgemmParams::ln_mode). Producer: residual GEMM whose f32 output feeds a LayerNorm; also emits the
+  // f16 copy `x16` and per-row partial statistics. Returns the number of statistic slots (0 in the measure pass).
+  static constexpr int kMaxLnSlots = 160;  // 2 * N / 16 for N = 1280
+  int linear_ln_producer(const __half* x, int M, const Lin& L, float* out, int ldo, const float* res, __half* x16, float2* stats) {
+    linear(x, M, L, IGEMM_LINEAR, out, 1, ldo, res, ldo);
+    if (err || P->ops.empty()) return 0;
+    IgemmParams& ig = P->ops.back().ig;
+    ig.ln_mode = 1; ig.ln_x16 = x16; ig.ln_stats = stats; ig.ln_rows = M;
+    if (A->measure) return 0;
+    const int slots = ig.tilesN * 2;
+    if (slots > kMaxLnSlots) { err = fail(c, 5006, "LayerNorm fold: %d statistic slots exceed %d", slots, kMaxLnSlots); return 0; }
+    ig.ln_slots = slots;
+    return slots;
+  }
+  // Consumer: the Linear that follows the LayerNorm (weights folded at load, Lin::ln_u / ln_v); A operand = the producer's x16.
+  void linear_ln_consumer(const __half* x16, int M, const Lin& L, int mode, void* out, int ldo, const float2* stats, int slots) {
+    linear(x16, M, L, mode, out, 0, ldo, nullptr, 0);
+    if (err || P->ops.empty()) return;
+    IgemmParams& ig = P->ops.back().ig;
+    ig.ln_mode = 2; ig.ln_stats = const_cast<float2*>(stats); ig.ln_rows = M; ig.ln_slots = slots;
+    ig.ln_u = L.ln_u; ig.ln_v = L.ln_v; ig.ln_inv_c = 1.0f / (float)L.K; ig.ln_eps = L.ln_eps;
+    ig.bias = nullptr;  // absorbed into ln_v
   }
   // 3x3 stride-1 conv (+ optional fused 1x1 skip segment on a1)
   void conv3(const ActView& a, const ActView* skip, const Conv& cv, float* out, const float* bias, int bias_bstride,

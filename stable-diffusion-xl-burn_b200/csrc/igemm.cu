@@ -163,9 +163,14 @@ __device__ __forceinline__ EpiPrefetch epi_prefetch(const IgemmParams& p, const 
   return f;
 }
 
+// LayerNorm fold (IgemmParams::ln_mode): producer-side running row sums in the phase-2 mapping, consumer-side row statistics
+struct LnAcc { float s[8], q[8]; };
+struct LnRow { float mean, rstd; };
+
 // one 32-column block (or a 16-column tail when ncols == 16) of the LINEAR epilogue; `pf` was issued earlier
+template <int LN>
 __device__ __forceinline__ void epi_linear_block(const IgemmParams& p, float* stage, uint32_t taddr, int n, int ncols,
-                                                 const EpiRows& rows, const EpiPrefetch& pf, int lane) {
+                                                 const EpiRows& rows, const EpiPrefetch& pf, int lane, LnAcc& la, const LnRow& lr) {
   // ---- phase 1: TMEM -> registers -> smem, lane = row
   const bool dbgb = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 64 && p.dbg[9] == 0;
   if (dbgb) p.dbg[9] = globaltimer_ns();
@@ -179,6 +184,21 @@ __device__ __forceinline__ void epi_linear_block(const IgemmParams& p, float* st
   }
   tmem_ld_wait();
   if (dbgb) p.dbg[10] = globaltimer_ns();
+  if constexpr (LN == 2) {
+    // consumer: normalise algebraically, lane = row. u/v are read as warp-wide broadcasts.
+    const float mr = lr.mean * lr.rstd;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (4 * i < ncols) {
+        const float4 u4 = __ldg(reinterpret_cast<const float4*>(p.ln_u + n) + i);
+        const float4 v4 = __ldg(reinterpret_cast<const float4*>(p.ln_v + n) + i);
+        v[4 * i] = __float_as_uint(fmaf(lr.rstd, __uint_as_float(v[4 * i]), fmaf(-mr, u4.x, v4.x)));
+        v[4 * i + 1] = __float_as_uint(fmaf(lr.rstd, __uint_as_float(v[4 * i + 1]), fmaf(-mr, u4.y, v4.y)));
+        v[4 * i + 2] = __float_as_uint(fmaf(lr.rstd, __uint_as_float(v[4 * i + 2]), fmaf(-mr, u4.z, v4.z)));
+        v[4 * i + 3] = __float_as_uint(fmaf(lr.rstd, __uint_as_float(v[4 * i + 3]), fmaf(-mr, u4.w, v4.w)));
+      }
+    }
+  }
   float* myrow = stage + lane * kStagePitch;
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -201,6 +221,16 @@ __device__ __forceinline__ void epi_linear_block(const IgemmParams& p, float* st
       f.z += b4.z + pf.res[it].z;
       f.w += b4.w + pf.res[it].w;
       const uint32_t off = rows.off[it] + (uint32_t)n;
+      if constexpr (LN == 1) {
+        // producer: the next LayerNorm's row statistics and the f16 copy that the consumer GEMM reads as its A operand
+        la.s[it] += (f.x + f.y) + (f.z + f.w);
+        la.q[it] += fmaf(f.x, f.x, f.y * f.y) + fmaf(f.z, f.z, f.w * f.w);
+        __half2 a16 = __floats2half2_rn(f.x, f.y), b16 = __floats2half2_rn(f.z, f.w);
+        uint2 o16;
+        o16.x = *reinterpret_cast<uint32_t*>(&a16);
+        o16.y = *reinterpret_cast<uint32_t*>(&b16);
+        *reinterpret_cast<uint2*>(p.ln_x16 + off) = o16;
+      }
       if (p.dbg_mode == 3) {
         if (f.x == 123.456f) reinterpret_cast<float*>(p.out)[0] = f.y + f.z + f.w;  // keep the math alive, no store traffic
       } else if (p.out_f32) {
@@ -219,8 +249,9 @@ __device__ __forceinline__ void epi_linear_block(const IgemmParams& p, float* st
 }
 
 // GEGLU block: 32 value columns at taddr_v, the matching 32 gate columns at taddr_g -> 32 f16 outputs
+template <int LN>
 __device__ __forceinline__ void epi_geglu_block(const IgemmParams& p, float* stage, uint32_t taddr_v, uint32_t taddr_g, int nv,
-                                                int ng, int ncol_out, const EpiRow& me, uint32_t ok_mask, int lane) {
+                                                int ng, int ncol_out, const EpiRow& me, uint32_t ok_mask, int lane, const LnRow& lr) {
   uint32_t v[32], g[32];
   tmem_ld32(taddr_v, v);
   tmem_ld32(taddr_g, g);
@@ -232,7 +263,15 @@ __device__ __forceinline__ void epi_geglu_block(const IgemmParams& p, float* sta
                            __uint_as_float(v[4 * i + 3]));
     float4 y = make_float4(__uint_as_float(g[4 * i]), __uint_as_float(g[4 * i + 1]), __uint_as_float(g[4 * i + 2]),
                            __uint_as_float(g[4 * i + 3]));
-    if (p.bias != nullptr) {
+    if constexpr (LN == 2) {
+      const float mr = lr.mean * lr.rstd;
+      const float4 ux = __ldg(reinterpret_cast<const float4*>(p.ln_u + nv) + i), vx = __ldg(reinterpret_cast<const float4*>(p.ln_v + nv) + i);
+      const float4 uy = __ldg(reinterpret_cast<const float4*>(p.ln_u + ng) + i), vy = __ldg(reinterpret_cast<const float4*>(p.ln_v + ng) + i);
+      x.x = fmaf(lr.rstd, x.x, fmaf(-mr, ux.x, vx.x)); x.y = fmaf(lr.rstd, x.y, fmaf(-mr, ux.y, vx.y));
+      x.z = fmaf(lr.rstd, x.z, fmaf(-mr, ux.z, vx.z)); x.w = fmaf(lr.rstd, x.w, fmaf(-mr, ux.w, vx.w));
+      y.x = fmaf(lr.rstd, y.x, fmaf(-mr, uy.x, vy.x)); y.y = fmaf(lr.rstd, y.y, fmaf(-mr, uy.y, vy.y));
+      y.z = fmaf(lr.rstd, y.z, fmaf(-mr, uy.z, vy.z)); y.w = fmaf(lr.rstd, y.w, fmaf(-mr, uy.w, vy.w));
+    } else if (p.bias != nullptr) {
       const float4 bx = __ldg(reinterpret_cast<const float4*>(p.bias + nv) + i);
       const float4 by = __ldg(reinterpret_cast<const float4*>(p.bias + ng) + i);
       x.x += bx.x; x.y += bx.y; x.z += bx.z; x.w += bx.w;
@@ -289,9 +328,16 @@ __device__ __forceinline__ void epi_linear_range(int BN, int half, int& b0, int&
 
 // Epilogue of one 128 x BN accumulator tile for one warp (32 rows, `half` selects which column blocks it owns).
 // `pf0` = prefetched operands of the warp's first LINEAR block (issued before the accumulator was complete).
+template <int LN>
 __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, float* stage, uint32_t trow, int nt, int n0,
-                                              const EpiRow& me, const EpiRows& rows, EpiPrefetch pf0, int half, int lane) {
+                                              const EpiRow& me, const EpiRows& rows, EpiPrefetch pf0, int half, int lane,
+                                              const LnRow& lr) {
   const int BN = p.BN;
+  LnAcc la;
+  if constexpr (LN == 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { la.s[i] = 0.f; la.q[i] = 0.f; }
+  }
   if (p.mode == IGEMM_LINEAR) {
     if ((p.N & 15) == 0) {
       // column blocks of 32 (+ one 16-wide tail when BN % 32 == 16), split between the two warps of a lane quarter
@@ -306,7 +352,7 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, float* stage
           const int c2 = (bI + 1) << 5;
           nxt = epi_prefetch(p, rows, n0 + c2, (BN - c2) >= 32 ? 32 : 16, lane);
         }
-        if (n0 + c < p.N) epi_linear_block(p, stage, trow + c, n0 + c, ncols, rows, pf, lane);
+        if (n0 + c < p.N) epi_linear_block<LN>(p, stage, trow + c, n0 + c, ncols, rows, pf, lane, la, lr);
         pf = nxt;
       }
     } else if (half == 0) {
@@ -340,11 +386,30 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, float* stage
     const int b0 = half == 0 ? 0 : ((nb + 1) >> 1), b1 = half == 0 ? ((nb + 1) >> 1) : nb;
     for (int bI = b0; bI < b1; ++bI) {
       const int c = bI << 5;
-      epi_geglu_block(p, stage, trow + c, trow + hb + c, n0 + c, n0 + hb + c, nt * hb + c, me, ok_mask, lane);
+      epi_geglu_block<LN>(p, stage, trow + c, trow + hb + c, n0 + c, n0 + hb + c, nt * hb + c, me, ok_mask, lane, lr);
     }
+  }
+  if constexpr (LN == 1) {
+    // la.s[it] / la.q[it]: this lane's 4 columns of row it*4 + (lane>>3), summed over the warp's column blocks.
+    // Reduce over the 8 lanes that share a row, then hand row L's totals to lane L (lane = row) and store the partial.
+    float S = 0.f, Q = 0.f;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      float a = la.s[it], b = la.q[it];
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      const float ta = __shfl_sync(0xffffffffu, a, (lane & 3) << 3);
+      const float tb = __shfl_sync(0xffffffffu, b, (lane & 3) << 3);
+      if ((lane >> 2) == it) { S = ta; Q = tb; }
+    }
+    if (me.ok) p.ln_stats[(size_t)me.pix * p.ln_slots + (nt * 2 + half)] = make_float2(S, Q);
   }
 }
 
+template <int LN>
 __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages x (A 16KB | B BN*128)] [full][empty][tmem_full x2][tmem_empty x2][tmem ptr]
@@ -519,11 +584,31 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
           pf0.bias = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
+      LnRow lr{0.f, 0.f};
+      if constexpr (LN == 2) {
+        // row statistics of the LayerNorm that was folded into this GEMM, from the producer's per-column-block partials
+        // stats layout [row][slot]: a lane reads its row's slots as independent 16-byte loads (8 in flight), then sums them in
+        // slot order (deterministic)
+        float sS = 0.f, sQ = 0.f;
+        if (me.ok) {
+          const float4* sp = reinterpret_cast<const float4*>(p.ln_stats + (size_t)me.pix * p.ln_slots);
+          const int n4 = p.ln_slots >> 1;
+          for (int k0 = 0; k0 < n4; k0 += 8) {
+            float4 t[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t[j] = (k0 + j < n4) ? __ldg(sp + k0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { sS += t[j].x; sQ += t[j].y; sS += t[j].z; sQ += t[j].w; }
+          }
+        }
+        lr.mean = sS * p.ln_inv_c;
+        lr.rstd = rsqrtf(fmaxf(fmaf(-lr.mean, lr.mean, sQ * p.ln_inv_c), 0.f) + p.ln_eps);
+      }
       mbar_wait(&tmem_full[buf], (lt >> 1) & 1);
       if (dbg && lt == 0 && threadIdx.x == 64) p.dbg[3] = globaltimer_ns();  // first accumulator complete
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
-      epilogue_tile(p, stage_buf, trow, nt, nt * BN, me, rows, pf0, half, lane);
+      epilogue_tile<LN>(p, stage_buf, trow, nt, nt * BN, me, rows, pf0, half, lane, lr);
       if (dbg && lt == 0 && threadIdx.x == 64) p.dbg[4] = globaltimer_ns();  // first epilogue done
       // all TMEM reads of this buffer are complete (tcgen05.wait::ld above): hand it back to the MMA warp
       tc_fence_before();
@@ -603,6 +688,7 @@ __device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {  // arrive on `b
                : "memory");
 }
 
+template <int LN>
 __global__ void __launch_bounds__(kThreads, 1) igemm_pair_kernel(const __grid_constant__ IgemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -762,11 +848,31 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_pair_kernel(const __grid_co
           pf0.bias = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
+      LnRow lr{0.f, 0.f};
+      if constexpr (LN == 2) {
+        // row statistics of the LayerNorm that was folded into this GEMM, from the producer's per-column-block partials
+        // stats layout [row][slot]: a lane reads its row's slots as independent 16-byte loads (8 in flight), then sums them in
+        // slot order (deterministic)
+        float sS = 0.f, sQ = 0.f;
+        if (me.ok) {
+          const float4* sp = reinterpret_cast<const float4*>(p.ln_stats + (size_t)me.pix * p.ln_slots);
+          const int n4 = p.ln_slots >> 1;
+          for (int k0 = 0; k0 < n4; k0 += 8) {
+            float4 t[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t[j] = (k0 + j < n4) ? __ldg(sp + k0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { sS += t[j].x; sQ += t[j].y; sS += t[j].z; sQ += t[j].w; }
+          }
+        }
+        lr.mean = sS * p.ln_inv_c;
+        lr.rstd = rsqrtf(fmaxf(fmaf(-lr.mean, lr.mean, sQ * p.ln_inv_c), 0.f) + p.ln_eps);
+      }
       mbar_wait(&tmem_full[buf], (lt >> 1) & 1);
       if (dbg && lt == 0 && threadIdx.x == 64) p.dbg[3] = globaltimer_ns();  // first accumulator complete
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
-      epilogue_tile(p, stage_buf, trow, nt, nt * BN, me, rows, pf0, half, lane);
+      epilogue_tile<LN>(p, stage_buf, trow, nt, nt * BN, me, rows, pf0, half, lane, lr);
       if (dbg && lt == 0 && threadIdx.x == 64) p.dbg[4] = globaltimer_ns();  // first epilogue done
       tc_fence_before();
       __syncwarp();
@@ -991,10 +1097,16 @@ int igemm_launch(cudaStream_t st, IgemmParams& p) {
   if (p.res != nullptr && p.ldr != p.ldo) return 1003;
   if ((unsigned long long)p.Bn * p.H * p.W * (unsigned long long)p.ldo >= (1ull << 32)) return 1004;
   const size_t smem = igemm_smem_bytes(p.nstages, p.pair ? p.BN / 2 : p.BN);
+  if (p.ln_mode < 0 || p.ln_mode > 2) return 1005;
+  if (p.ln_mode && ((p.N & 15) || !p.ln_stats || p.ln_rows <= 0)) return 1006;
+  if (p.ln_mode == 1 && (!p.ln_x16 || !p.out_f32 || p.mode != IGEMM_LINEAR)) return 1007;
+  if (p.ln_mode == 2 && (!p.ln_u || !p.ln_v || p.ln_slots <= 0 || p.res != nullptr)) return 1008;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(igemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaSuccess;
+    const void* fns[6] = {(const void*)igemm_kernel<0>, (const void*)igemm_kernel<1>, (const void*)igemm_kernel<2>,
+                          (const void*)igemm_pair_kernel<0>, (const void*)igemm_pair_kernel<1>, (const void*)igemm_pair_kernel<2>};
+    for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
@@ -1015,7 +1127,7 @@ int igemm_launch(cudaStream_t st, IgemmParams& p) {
       at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
       int q = 0;
-      if (cudaOccupancyMaxActiveClusters(&q, igemm_kernel, &cfg) == cudaSuccess && q > 0) n = q;
+      if (cudaOccupancyMaxActiveClusters(&q, igemm_kernel<0>, &cfg) == cudaSuccess && q > 0) n = q;
       else cudaGetLastError();
     }
     max_clusters[cs] = n;
@@ -1034,8 +1146,16 @@ int igemm_launch(cudaStream_t st, IgemmParams& p) {
     p.fd_wh = recip(m_tiles, (unsigned long long)p.tilesW * p.tilesH);
     p.fd_h = 0;
   }
-  if (p.pair) return launch_kernel_cluster(igemm_pair_kernel, dim3(nclusters * 2), dim3(kThreads), smem, st, true, 2, p);
-  return launch_kernel_cluster(igemm_kernel, dim3(nclusters * cs), dim3(kThreads), smem, st, true, cs, p);
+  if (p.pair) {
+    const dim3 g(nclusters * 2), b(kThreads);
+    if (p.ln_mode == 1) return launch_kernel_cluster(igemm_pair_kernel<1>, g, b, smem, st, true, 2, p);
+    if (p.ln_mode == 2) return launch_kernel_cluster(igemm_pair_kernel<2>, g, b, smem, st, true, 2, p);
+    return launch_kernel_cluster(igemm_pair_kernel<0>, g, b, smem, st, true, 2, p);
+  }
+  const dim3 g(nclusters * cs), b(kThreads);
+  if (p.ln_mode == 1) return launch_kernel_cluster(igemm_kernel<1>, g, b, smem, st, true, cs, p);
+  if (p.ln_mode == 2) return launch_kernel_cluster(igemm_kernel<2>, g, b, smem, st, true, cs, p);
+  return launch_kernel_cluster(igemm_kernel<0>, g, b, smem, st, true, cs, p);
 }
 
 }  // namespace sdxl

@@ -88,6 +88,18 @@ struct alignas(64) IgemmParams {
   int bias_bstride;
   const float* res;           // nullable f32 residual [pixels, ldr]
   int ldr;
+  // LayerNorm folded into the GEMMs around it (no separate LayerNorm pass, see DESIGN.md "LayerNorm fold"):
+  //   ln_mode 1 (producer, residual GEMM whose f32 output is the next LayerNorm's input): also writes the f16 copy of the
+  //     output (the consumer's A operand) and per-row partial (sum, sum of squares) of its columns into
+  //     ln_stats[row * ln_slots + (n_tile*2 + half)];
+  //   ln_mode 2 (consumer, weights pre-multiplied by gamma): out = rstd_r * (acc - mean_r * ln_u[n]) + ln_v[n], with
+  //     mean/rstd of row r from the ln_slots partials; ln_u[n] = sum_k W'[n,k], ln_v[n] = sum_k beta_k W[n,k] + bias[n].
+  int ln_mode;
+  __half* ln_x16;             // producer: f16 copy of the output, same leading dimension as out
+  float2* ln_stats;           // [ln_rows, ln_slots] (ln_slots even, 16-byte aligned rows)
+  int ln_slots, ln_rows;
+  const float* ln_u; const float* ln_v;   // consumer, [N] (GEGLU: in the fused [value|gate] column order)
+  float ln_inv_c, ln_eps;     // consumer: 1 / (normalised width), eps
   // host-computed reciprocals (floor(2^32/d)+1; q = umulhi(n, m), exact while n*d < 2^32; 0 = use '/') for the tile-index
   // divisions of the producer warp: on the critical path between griddepcontrol.wait and the first TMA issue
   unsigned fd_pm, fd_w, fd_h, fd_wh;   // divisors: pair M tiles (or M tiles), tilesW, tilesH, tilesW*tilesH
@@ -237,6 +249,10 @@ int transpose_linear_launch(cudaStream_t st, const __half* src, int K, int N, __
 int repack_conv_launch(cudaStream_t st, const __half* src, int O, int I, int KH, int KW, __half* dst,
                        int Ktot, int col0, int Ipad);
 int vec_add_f32_launch(cudaStream_t st, float* dst, const float* src, int n);  // dst += src
+// LayerNorm fold into a K-major Linear weight [N, Kpad] (in place): W <- f16(gamma[k] W), u[n] = sum_k W'[n,k],
+// v[n] = sum_k beta[k] W[n,k] + bias[n] (bias nullable).
+int ln_fold_launch(cudaStream_t st, __half* W, int N, int K, int Kpad, const float* gamma, const float* beta, const float* bias,
+                   float* u, float* v);
 // bias f16 [N] -> f32, optional GEGLU permutation, optional accumulate (dst += src).
 int bias_to_f32_launch(cudaStream_t st, const __half* src, int N, float* dst, int geglu_bn, int accumulate);
 

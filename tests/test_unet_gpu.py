@@ -188,3 +188,31 @@ def test_error_paths(ctx, tiny):
     del bad["middle_block/res1/conv_in/weight"]
     with pytest.raises(SdxlError):
         Diffuser(ctx, TINY, bad)
+
+
+def test_layernorm_fold_path_parity():
+    """The experimental LayerNorm-fold epilogues (SDXL_B200_LN_FOLD=1, read once at load time -> separate process): same oracle
+    bound as the default path."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, os, torch\n"
+        "sys.path.insert(0, os.path.join(os.getcwd(), 'stable-diffusion-xl-burn_b200')); sys.path.insert(0, os.getcwd())\n"
+        "import sdxl_b200\n"
+        "from oracle import unet_oracle as O\n"
+        "cfg = sdxl_b200.TINY; w = sdxl_b200.synth_weights(cfg, seed=0)\n"
+        "ctx = sdxl_b200.Context(0); d = sdxl_b200.Diffuser(ctx, cfg, w)\n"
+        "g = torch.Generator().manual_seed(0)\n"
+        "x = torch.randn(2, 4, 16, 16, generator=g); c = torch.randn(2, 77, cfg.context_dim, generator=g).half().float()\n"
+        "y = torch.randn(2, cfg.adm_in_channels, generator=g).half().float()\n"
+        "out = d.unet_forward(x, [499], c, y).cpu()\n"
+        "ref = O.unet_forward(cfg, O.to_f32(w), x, torch.tensor([499]), c, y)\n"
+        "print('FOLD_REL_ERR', float((out - ref).norm() / ref.norm()))\n"
+    )
+    env = dict(os.environ, SDXL_B200_LN_FOLD="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    err = float([ln for ln in r.stdout.splitlines() if ln.startswith("FOLD_REL_ERR")][0].split()[1])
+    print("LayerNorm-fold path rel err", err)
+    assert err <= FWD_TOL
