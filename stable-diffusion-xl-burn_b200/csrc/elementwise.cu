@@ -433,6 +433,35 @@ int repack_conv_launch(cudaStream_t st, const __half* src, int O, int I, int KH,
   repack_conv_kernel<<<grid, 256, 0, st>>>(src, O, I, KH, KW, dst, Ktot, col0, Ipad);
   return (int)cudaGetLastError();
 }
+// Nearest-2x upsample followed by a 3x3 pad-1 conv (reference unet/mod.rs:742-751, autoencoder/mod.rs:311-319): output pixel
+// (2i+a, 2j+b) reads upsampled rows 2i+a-1 .. 2i+a+1 = source rows {i-1, i, i} for a = 0 and {i, i, i+1} for a = 1 (same for
+// columns), so each output parity (a, b) is a 2x2 convolution of the source image with summed taps:
+//   a = 0: tap th=0 (dh=-1) = kh{0},   th=1 (dh=0)  = kh{1,2};     a = 1: th=0 (dh=0) = kh{0,1},   th=1 (dh=+1) = kh{2}
+__global__ void repack_upconv_kernel(const __half* __restrict__ src, int O, int I, __half* __restrict__ dst, int Ipad) {
+  const long total = (long)4 * O * 4 * Ipad;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % Ipad);
+    const int tap = (int)((idx / Ipad) % 4);
+    const int o = (int)((idx / ((long)Ipad * 4)) % O);
+    const int ph = (int)(idx / ((long)Ipad * 4 * O));
+    const int a = ph >> 1, b = ph & 1, th = tap >> 1, tw = tap & 1;
+    float acc = 0.f;
+    if (i < I) {
+      const int kh0 = a == 0 ? (th == 0 ? 0 : 1) : (th == 0 ? 0 : 2), kh1 = a == 0 ? (th == 0 ? 0 : 2) : (th == 0 ? 1 : 2);
+      const int kw0 = b == 0 ? (tw == 0 ? 0 : 1) : (tw == 0 ? 0 : 2), kw1 = b == 0 ? (tw == 0 ? 0 : 2) : (tw == 0 ? 1 : 2);
+      for (int kh = kh0; kh <= kh1; ++kh)
+        for (int kw = kw0; kw <= kw1; ++kw) acc += __half2float(src[(((size_t)o * I + i) * 3 + kh) * 3 + kw]);
+    }
+    dst[idx] = __float2half_rn(acc);
+  }
+}
+int repack_upconv_launch(cudaStream_t st, const __half* src, int O, int I, __half* dst, int Ipad) {
+  const long total = (long)4 * O * 4 * Ipad;
+  int grid = cdiv(total, 256);
+  if (grid > 148 * 32) grid = 148 * 32;
+  repack_upconv_kernel<<<grid, 256, 0, st>>>(src, O, I, dst, Ipad);
+  return (int)cudaGetLastError();
+}
 __global__ void bias_to_f32_kernel(const __half* __restrict__ src, int N, float* __restrict__ dst, int geglu_bn,
                                    int accumulate) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;

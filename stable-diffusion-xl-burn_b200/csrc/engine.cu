@@ -296,7 +296,7 @@ static int build_model(sdxl_unet* u, const PackView& pv, Arena& A) {
         b.res = load_res(L, bp + "/res", cins[k], cout, ted, tembs, temb_total);
         b.st = load_st(L, bp + "/transformer", cout, g.context_dim, n_head(cout), g.transformer_depths[level]);
       }
-      if (up) b.conv = L.conv(bp + "/upsample/conv", cout, cout, 3);
+      if (up) b.conv = L.upconv(bp + "/upsample/conv", cout, cout);
       u->out_blocks.push_back(std::move(b));
     }
   }
@@ -641,16 +641,11 @@ static int build_plan_ops(sdxl_unet* u, Plan* P, Arena* A) {
     Cx = b.res.Cout;
     if (b.type == BT_REST || b.type == BT_RESTU) x = B.strans(b.st, x, H, W, s_a16, s_tok, s_qkv, s_ao, s_q, s_ff, s_x16, s_stats);
     if (b.type == BT_RESTU || b.type == BT_RESU) {
-      // nearest-2x then 3x3 conv (unet/mod.rs:742-751)
-      __half* up = B.buf<__half>((size_t)Bf * 4 * H * W * Cx);
-      Op op{};
-      op.kind = OP_UPS;
-      op.rs = {x, Bf, H, W, Cx, up};
-      P->ops.push_back(op);
+      // nearest-2x then 3x3 conv (unet/mod.rs:742-751), as four 2x2 phase convolutions of the source image
+      __half* x16 = B.buf<__half>((size_t)Bf * H * W * Cx);
+      float* y = B.buf<float>((size_t)Bf * 4 * H * W * Cx);
+      B.upconv(x, Bf, H, W, b.conv, x16, y);
       H *= 2; W *= 2;
-      ActView a{up, Bf, H, W, Cx};
-      float* y = B.buf<float>((size_t)Bf * H * W * Cx);
-      B.conv3(a, nullptr, b.conv, y, b.conv.b, 0, nullptr);
       x = y;
     }
   }

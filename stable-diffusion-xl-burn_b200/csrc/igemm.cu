@@ -567,7 +567,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       const int bb = tb * p.Bt + bt, hh = th * p.Ht + ht, ww = tw * p.Wt + wt;
       EpiRow me;
       me.ok = (bb < p.Bn) && (hh < p.H) && (ww < p.W);
-      me.pix = me.ok ? ((size_t)bb * p.H + hh) * p.W + ww : 0;
+      me.pix = me.ok ? ((size_t)bb * p.H + hh) * (size_t)p.opix_row + (size_t)ww * p.opix_w + p.opix_off : 0;
       me.bb = me.ok ? bb : 0;
       const int buf = lt & 1;
       // row descriptors + the first block's residual/bias are fetched while the MMAs of this tile still run
@@ -831,7 +831,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_pair_kernel(const __grid_co
       const int bb = tb * p.Bt + bt, hh = th * p.Ht + ht, ww = tw * p.Wt + wt;
       EpiRow me;
       me.ok = (bb < p.Bn) && (hh < p.H) && (ww < p.W);
-      me.pix = me.ok ? ((size_t)bb * p.H + hh) * p.W + ww : 0;
+      me.pix = me.ok ? ((size_t)bb * p.H + hh) * (size_t)p.opix_row + (size_t)ww * p.opix_w + p.opix_off : 0;
       me.bb = me.ok ? bb : 0;
       const int buf = lt & 1;
       // row descriptors + the first block's residual/bias are fetched while the MMAs of this tile still run
@@ -1038,6 +1038,7 @@ int igemm_configure(IgemmParams& p, const IgemmOperands& o, int outW, int outH, 
   if (total_kb < 1) total_kb = 1;
   igemm_pick_box(outW, outH, &p.Wt, &p.Ht, &p.Bt);
   p.W = outW; p.H = outH; p.Bn = outB;
+  p.opix_row = outW; p.opix_w = 1; p.opix_off = 0;
   p.tilesW = (outW + p.Wt - 1) / p.Wt;
   p.tilesH = (outH + p.Ht - 1) / p.Ht;
   p.tilesB = (outB + p.Bt - 1) / p.Bt;
@@ -1095,7 +1096,7 @@ int igemm_configure(IgemmParams& p, const IgemmOperands& o, int outW, int outH, 
 int igemm_launch(cudaStream_t st, IgemmParams& p) {
   // the epilogue addresses outputs with 32-bit element offsets and shares the leading dimension with the residual
   if (p.res != nullptr && p.ldr != p.ldo) return 1003;
-  if ((unsigned long long)p.Bn * p.H * p.W * (unsigned long long)p.ldo >= (1ull << 32)) return 1004;
+  if ((unsigned long long)p.Bn * p.H * (unsigned long long)p.opix_row * (unsigned long long)p.ldo >= (1ull << 32)) return 1004;
   const size_t smem = igemm_smem_bytes(p.nstages, p.pair ? p.BN / 2 : p.BN);
   if (p.ln_mode < 0 || p.ln_mode > 2) return 1005;
   if (p.ln_mode && ((p.N & 15) || !p.ln_stats || p.ln_rows <= 0)) return 1006;

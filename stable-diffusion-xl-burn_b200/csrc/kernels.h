@@ -88,6 +88,10 @@ struct alignas(64) IgemmParams {
   int bias_bstride;
   const float* res;           // nullable f32 residual [pixels, ldr]
   int ldr;
+  // output pixel of tile pixel (b, h, w): (b*H + h) * opix_row + w * opix_w + opix_off (defaults W, 1, 0). The nearest-2x
+  // upsample + 3x3 conv is run as four 2x2 convolutions on the original image, each writing one (row, column) parity of the
+  // upsampled output: opix_row = 4W, opix_w = 2, opix_off = a*2W + b.
+  int opix_row, opix_w, opix_off;
   // LayerNorm folded into the GEMMs around it (no separate LayerNorm pass, see DESIGN.md "LayerNorm fold"):
   //   ln_mode 1 (producer, residual GEMM whose f32 output is the next LayerNorm's input): also writes the f16 copy of the
   //     output (the consumer's A operand) and per-row partial (sum, sum of squares) of its columns into
@@ -248,6 +252,9 @@ int transpose_linear_launch(cudaStream_t st, const __half* src, int K, int N, __
 // Conv OIHW f16 -> [O, (kh,kw,I padded to Ipad)] f16 at column offset col0 of a [O, Ktot] matrix.
 int repack_conv_launch(cudaStream_t st, const __half* src, int O, int I, int KH, int KW, __half* dst,
                        int Ktot, int col0, int Ipad);
+// 3x3 conv that follows a nearest-2x upsample -> four 2x2 phase kernels on the original image (sums of the 3x3 taps that
+// read the same source pixel, added in f32, rounded once): dst [4 (a*2+b)][O][4 (th*2+tw) * Ipad].
+int repack_upconv_launch(cudaStream_t st, const __half* src, int O, int I, __half* dst, int Ipad);
 int vec_add_f32_launch(cudaStream_t st, float* dst, const float* src, int n);  // dst += src
 // LayerNorm fold into a K-major Linear weight [N, Kpad] (in place): W <- f16(gamma[k] W), u[n] = sum_k W'[n,k],
 // v[n] = sum_k beta[k] W[n,k] + bias[n] (bias nullable).

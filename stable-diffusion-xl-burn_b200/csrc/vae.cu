@@ -134,7 +134,7 @@ static int build_vae(sdxl_vae* v, const PackView& pv, Arena& A) {
     b.r[1] = load_vres(L, bp + "/res2", co, co);
     b.r[2] = load_vres(L, bp + "/res3", co, co);
     b.up = (i != g.n_blocks - 1);
-    if (b.up) b.upc = L.conv(bp + "/upsampler", co, co, 3);
+    if (b.up) b.upc = L.upconv(bp + "/upsampler", co, co);
     v->blocks.push_back(b);
   }
   if (L.err) return L.err;
@@ -361,7 +361,7 @@ static int build_vae_plan(sdxl_vae* v, Plan* P, Arena* A) {
         max_in = std::max(max_in, (size_t)hh * ww * b.r[k].Cin);
         max_out = std::max(max_out, (size_t)hh * ww * b.r[k].Cout);
       }
-      if (b.up) { hh *= 2; ww *= 2; max_up = std::max(max_up, (size_t)hh * ww * b.Cout); }
+      if (b.up) { max_up = std::max(max_up, (size_t)hh * ww * b.Cout); hh *= 2; ww *= 2; }
       max_x = std::max(max_x, (size_t)hh * ww * b.Cout);
     }
     max_in = std::max(max_in, max_x);  // norm_out operand
@@ -397,14 +397,9 @@ static int build_vae_plan(sdxl_vae* v, Plan* P, Arena* A) {
     if (B.err) break;
     for (int k = 0; k < 3; ++k) st.vres(b.r[k]);
     if (b.up) {
-      // nearest-2x then 3x3 conv (autoencoder/mod.rs:311-319)
-      Op op{};
-      op.kind = OP_UPS;
-      op.rs = {st.x(), Bn, st.H, st.W, b.Cout, s_up};
-      P->ops.push_back(op);
+      // nearest-2x then 3x3 conv (autoencoder/mod.rs:311-319), as four 2x2 phase convolutions of the source image
+      B.upconv(st.x(), Bn, st.H, st.W, b.upc, s_up, st.other());
       st.H *= 2; st.W *= 2;
-      ActView a{s_up, Bn, st.H, st.W, b.Cout};
-      B.conv3(a, nullptr, b.upc, st.other(), b.upc.b, 0, nullptr);
       st.flip();
     }
   }
