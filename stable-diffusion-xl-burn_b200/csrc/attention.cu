@@ -11,6 +11,8 @@
 // per-block P V result is double-buffered in TMEM and folded into the register accumulator one block late, so
 // the softmax warps never wait for the tensor pipe in steady state and TMEM never needs a read-modify-write.
 // Warp roles (320 threads): warp0 TMA producer, warp1 MMA issuer + TMEM owner, warps 2..5 softmax A, 6..9 softmax B.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -18,8 +20,12 @@ namespace sdxl {
 
 static constexpr int kTileBytes = 128 * 128;        // 128 rows x 64 halves (Q, K or V tile)
 static constexpr int kPBytes = 2 * 128 * 128;       // 128 rows x 128 keys, two 64-key swizzle panels
-static constexpr int kAttnSmem = 2 * kTileBytes + 4 * kTileBytes + 2 * kPBytes + 256;
-static constexpr int kAttnThreads = 320;
+static constexpr int kXchgBytes = 2 * 2 * 2 * 128 * 4;  // SPLIT=2: [slot][group][column half][row] f32
+static constexpr int kAttnSmem = 2 * kTileBytes + 4 * kTileBytes + 2 * kPBytes + 256 + kXchgBytes;
+// SPLIT = threads per query row in the softmax groups: 1 -> warps 2..5 / 6..9 (320 threads),
+// 2 -> warps 2..9 / 10..17 (576 threads): each thread owns 64 of a block's 128 score columns and 32 of the 64 output columns,
+// twice as many warps per scheduler to cover the tcgen05.ld latency.
+template <int SPLIT> struct AttnCfg { static constexpr int kThreads = 64 + 256 * SPLIT; };
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -27,7 +33,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid_constant__ AttnParams p) {
+template <int SPLIT>
+__global__ void __launch_bounds__(AttnCfg<SPLIT>::kThreads, 1) attention_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;                       // [2] tiles A, B
   uint8_t* sK = sQ + 2 * kTileBytes;        // [2] stages
@@ -41,6 +48,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
   uint64_t* p_full = bars + 7;     // [2] per group, 128 arrivals
   uint64_t* pv_done = bars + 9;    // [2] per group
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 11);
+  float* xchg = reinterpret_cast<float*>(sP + 2 * kPBytes + 256);   // SPLIT=2 pair exchange slots
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nblk = (p.S + 127) / 128;
@@ -84,7 +92,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
+      mbar_init(&p_full[i], 128 * SPLIT);
       mbar_init(&pv_done[i], 1);
     }
     fence_barrier_init();
@@ -161,6 +169,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
       mbar_wait(&kv_empty[s], (uses - 1) & 1);
     }
   } else {
+    if constexpr (SPLIT == 1) {
     const int x = (warp - 2) >> 2;  // softmax group: 0 = tile A, 1 = tile B
     if (x == 0 || hasB) {
       const int q = warp & 3;
@@ -307,6 +316,138 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         }
       }
     }
+    } else {
+    // ---------- SPLIT == 2: two threads per query row ----------
+    const int sw = warp - 2;              // 0..15
+    const int x = sw >> 3;                // softmax group: 0 = tile A, 1 = tile B
+    if (x == 0 || hasB) {
+      const int q = warp & 3;             // TMEM lane quarter this warp may access (hardware: warp id % 4)
+      const int ch = (sw >> 2) & 1;       // column half: score columns [64 ch, 64 ch + 64), output columns [32 ch, 32 ch + 32)
+      const int r = q * 32 + lane;        // query row in tile == TMEM lane
+      const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+      const uint32_t tS = tmem_base + lane_off + x * 128 + ch * 64;
+      const uint32_t tO = tmem_base + lane_off + 256 + x * 128 + ch * 32;
+      const float sl2e = p.scale_log2e;
+      const int bar_id = 1 + x * 4 + q;   // named barrier of the two warps that share these 32 rows
+      int xk = 0;                         // exchange counter (slot = xk & 1)
+      // combine a per-thread value with the partner thread of the same row (other column half)
+      auto exchange = [&](float v) {
+        float* slot = xchg + (((xk & 1) * 2 + x) * 2) * 128;
+        slot[ch * 128 + r] = v;
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+        const float o = slot[(ch ^ 1) * 128 + r];
+        ++xk;
+        return o;
+      };
+      float m = -INFINITY, m_prev = -INFINITY, l = 0.f, alpha_prev = 0.f;
+      float O[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) O[i] = 0.f;
+      uint8_t* prow = sP + x * kPBytes + ch * (128 * 128) + (r >> 3) * 1024 + (r & 7) * 128;   // my 64-key panel
+      const int rx = r & 7;
+
+      for (int j = 0; j < nblk; ++j) {
+        mbar_wait(&s_full[x], j & 1);
+        if (j > 0) mbar_wait(&pv_done[x], (j - 1) & 1);
+        tc_fence_after();
+        const int kbase = j * 128 + ch * 64;
+        const bool ragged = j * 128 + 128 > p.S;
+        float ref = m;
+        if (j == 0) {
+          float mx = -INFINITY;
+#pragma unroll 1
+          for (int c = 0; c < 64; c += 32) {
+            uint32_t v[32];
+            tmem_ld32(tS + c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (!ragged || kbase + c + i < p.S) mx = fmaxf(mx, __uint_as_float(v[i]));
+          }
+          ref = fmaxf(mx, exchange(mx));
+        }
+        float alpha, sum, bmax;
+        bool redo;
+        do {
+          alpha = ex2_approx((m_prev - ref) * sl2e);
+          const float mb = ref * sl2e;
+          sum = 0.f;
+          float b0 = -INFINITY, b1 = -INFINITY;
+#pragma unroll 1
+          for (int c = 0; c < 64; c += 32) {
+            uint32_t v[32];
+            tmem_ld32(tS + c, v);
+            tmem_ld_wait();
+            uint32_t h[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
+              if (ragged) {
+                if (kbase + c + i >= p.S) s0 = -INFINITY;
+                if (kbase + c + i + 1 >= p.S) s1 = -INFINITY;
+              }
+              b0 = fmaxf(b0, s0);
+              b1 = fmaxf(b1, s1);
+              const float p0 = ex2_approx(fmaf(s0, sl2e, -mb));
+              const float p1 = ex2_approx(fmaf(s1, sl2e, -mb));
+              sum += p0 + p1;
+              __half2 t = __floats2half2_rn(p0, p1);
+              h[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
+            }
+            const int ch0 = c >> 3;  // first 16B chunk of this 32-key group inside my panel's 128B row
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              *reinterpret_cast<uint4*>(prow + (((ch0 + u) ^ rx) << 4)) = make_uint4(h[4 * u], h[4 * u + 1], h[4 * u + 2], h[4 * u + 3]);
+          }
+          const float bh = fmaxf(b0, b1);
+          bmax = fmaxf(bh, exchange(bh));   // block max of the whole row: both threads take identical decisions
+          const bool over = (bmax - ref) * sl2e > 15.0f;
+          redo = __any_sync(0xffffffffu, over);   // same rows in both warps of the pair -> same vote
+          if (over) ref = bmax;
+        } while (redo);
+        l = l * alpha + sum;   // partial sum over my columns; the halves are added once at the end
+        m_prev = ref;
+        m = ((bmax - ref) * sl2e > 8.0f) ? bmax : ref;
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(&p_full[x]);
+        if (j > 0) {
+          uint32_t v[32];
+          tmem_ld32(tO + ((j - 1) & 1) * 64, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) O[i] = fmaf(O[i], alpha_prev, __uint_as_float(v[i]));
+        }
+        alpha_prev = alpha;
+      }
+      {
+        const int j = nblk - 1;
+        mbar_wait(&pv_done[x], j & 1);
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld32(tO + (j & 1) * 64, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) O[i] = fmaf(O[i], alpha_prev, __uint_as_float(v[i]));
+      }
+      const float lt = l + exchange(l);
+      const int t = row0 + x * 128 + r;
+      if (t < p.T) {
+        const float inv = 1.0f / lt;
+        __half* o = p.out + ((size_t)b * p.T + t) * p.ldo + head * 64 + ch * 32;
+#pragma unroll
+        for (int c = 0; c < 32; c += 8) {
+          uint32_t h[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            __half2 t2 = __floats2half2_rn(O[c + 2 * i] * inv, O[c + 2 * i + 1] * inv);
+            h[i] = *reinterpret_cast<uint32_t*>(&t2);
+          }
+          *reinterpret_cast<uint4*>(o + c) = make_uint4(h[0], h[1], h[2], h[3]);
+        }
+      }
+    }
+    }
   }
 
   tc_fence_before();
@@ -318,9 +459,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
 }
 
 int attention_launch(cudaStream_t st, const AttnParams& p) {
+  // SDXL_B200_ATTN_SPLIT=2 selects the two-threads-per-row softmax (16 softmax warps); default 1
+  static const int split = (getenv("SDXL_B200_ATTN_SPLIT") && atoi(getenv("SDXL_B200_ATTN_SPLIT")) == 2) ? 2 : 1;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
     if (e != cudaSuccess) return (int)e;
     attr = true;
   }
@@ -334,7 +478,8 @@ int attention_launch(cudaStream_t st, const AttnParams& p) {
   const long tiles = (long)p.B * p.n_head * ((p.T + 127) / 128);
   const long want = (tiles + 1) / 2;  // one pair per CTA when the machine is not full
   dim3 grid((unsigned)(want < num_sms ? (want > 0 ? want : 1) : num_sms));
-  return launch_kernel(attention_kernel, grid, dim3(kAttnThreads), (size_t)kAttnSmem, st, true, p);
+  if (split == 2) return launch_kernel(attention_kernel<2>, grid, dim3(AttnCfg<2>::kThreads), (size_t)kAttnSmem, st, true, p);
+  return launch_kernel(attention_kernel<1>, grid, dim3(AttnCfg<1>::kThreads), (size_t)kAttnSmem, st, true, p);
 }
 
 }  // namespace sdxl

@@ -160,3 +160,31 @@ def test_randn_matches_philox_oracle(ctx):
     ref = philox.randn(n, 0x1234_5678_9ABC, 7)
     assert np.abs(out - ref).max() < 1e-4  # identical integer stream; f32 log/sin/cos differ by ulps
     assert abs(out.mean()) < 0.01 and abs(out.std() - 1) < 0.01
+
+
+def test_attention_split_rows_variant_parity():
+    """The experimental two-threads-per-row softmax (SDXL_B200_ATTN_SPLIT=2, read once per process -> subprocess): same bound."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, os, torch\n"
+        "sys.path.insert(0, os.path.join(os.getcwd(), 'stable-diffusion-xl-burn_b200')); sys.path.insert(0, os.getcwd())\n"
+        "import sdxl_b200\n"
+        "from oracle import unet_oracle as O\n"
+        "ctx = sdxl_b200.Context(0); g = torch.Generator().manual_seed(0)\n"
+        "worst = 0.0\n"
+        "for (B, T, S, nh) in ((2, 1024, 1024, 4), (1, 300, 77, 2), (1, 256, 640, 3)):\n"
+        "    q = torch.randn(B, T, nh * 64, generator=g).half(); k = torch.randn(B, S, nh * 64, generator=g).half(); v = torch.randn(B, S, nh * 64, generator=g).half()\n"
+        "    out = ctx.qkv_attention(q, k, v, None, nh).float().cpu()\n"
+        "    ref = O.qkv_attention(q.float(), k.float(), v.float(), None, nh)\n"
+        "    worst = max(worst, float((out - ref).norm() / ref.norm()))\n"
+        "print('SPLIT_REL_ERR', worst)\n"
+    )
+    env = dict(os.environ, SDXL_B200_ATTN_SPLIT="2")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    err = float([ln for ln in r.stdout.splitlines() if ln.startswith("SPLIT_REL_ERR")][0].split()[1])
+    print("split-row attention rel err", err)
+    assert err < 2e-3
