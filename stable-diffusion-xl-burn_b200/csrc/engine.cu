@@ -180,11 +180,8 @@ static STrans load_st(Loader& L, const std::string& path, int C, int ctx_dim, in
     if (!gbn) { L.err = fail(L.c, 4009, "GEGLU width %d not tileable", 4 * C); break; }
     b.ff1 = L.linear(bp + "/mlp/geglu/proj", C, 8 * C, true, gbn);
     b.ff2 = L.linear(bp + "/mlp/lin", 4 * C, C, true);
-    // LayerNorm fold (EXPERIMENTAL, off by default: SDXL_B200_LN_FOLD=1): norm1 -> qkv, norm2 -> attn2/query, norm3 -> GEGLU
-    // projection (each LayerNorm has exactly one consumer, unet/mod.rs:885-891). Parity holds (tests/test_unet_gpu.py runs it in a
-    // subprocess) but the first implementation is slower than the separate LayerNorm passes (22.5 vs 21.0 ms per step: the
-    // consumer epilogue's u/v loads serialise and spill at the 168-register ceiling, +15 us on the qkv GEMM) and it gives up
-    // bit-exact batch invariance (tile-dependent partial-sum order); see profiles/README.md.
+    // LayerNorm fold (SDXL_B200_LN_FOLD=1; default decided by the measurements in profiles/README.md): norm1 -> qkv,
+    // norm2 -> attn2/query, norm3 -> GEGLU projection (each LayerNorm has exactly one consumer, unet/mod.rs:885-891).
     static const bool fold = getenv("SDXL_B200_LN_FOLD") != nullptr && atoi(getenv("SDXL_B200_LN_FOLD")) != 0;
     if (fold) {
       L.fold_ln(b.qkv, b.n1);

@@ -409,14 +409,13 @@ struct PlanBuilder {
   // f16 copy `x16` and per-row partial statistics. Returns the number of statistic slots (0 in the measure pass).
   static constexpr int kMaxLnSlots = 160;  // 2 * N / 16 for N = 1280
   int linear_ln_producer(const __half* x, int M, const Lin& L, float* out, int ldo, const float* res, __half* x16, float2* stats) {
+    // statistic slots are fixed 16-column groups of the output (independent of the tile shape: bit-exact batch invariance)
+    const int slots = L.N / 16;
+    if (L.N % 32 || slots > kMaxLnSlots) { if (!err) err = fail(c, 5006, "LayerNorm fold: width %d unsupported", L.N); return 0; }
     linear(x, M, L, IGEMM_LINEAR, out, 1, ldo, res, ldo);
     if (err || P->ops.empty()) return 0;
     IgemmParams& ig = P->ops.back().ig;
-    ig.ln_mode = 1; ig.ln_x16 = x16; ig.ln_stats = stats; ig.ln_rows = M;
-    if (A->measure) return 0;
-    const int slots = ig.tilesN * 2;
-    if (slots > kMaxLnSlots) { err = fail(c, 5006, "LayerNorm fold: %d statistic slots exceed %d", slots, kMaxLnSlots); return 0; }
-    ig.ln_slots = slots;
+    ig.ln_mode = 1; ig.ln_x16 = x16; ig.ln_stats = stats; ig.ln_rows = M; ig.ln_slots = slots;
     return slots;
   }
   // Consumer: the Linear that follows the LayerNorm (weights folded at load, Lin::ln_u / ln_v); A operand = the producer's x16.

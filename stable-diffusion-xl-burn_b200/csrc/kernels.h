@@ -94,8 +94,8 @@ struct alignas(64) IgemmParams {
   int opix_row, opix_w, opix_off;
   // LayerNorm folded into the GEMMs around it (no separate LayerNorm pass, see DESIGN.md "LayerNorm fold"):
   //   ln_mode 1 (producer, residual GEMM whose f32 output is the next LayerNorm's input): also writes the f16 copy of the
-  //     output (the consumer's A operand) and per-row partial (sum, sum of squares) of its columns into
-  //     ln_stats[row * ln_slots + (n_tile*2 + half)];
+  //     output (the consumer's A operand) and, per row, the (sum, sum of squares) of every 16-column group of the output
+  //     into ln_stats[row * ln_slots + column / 16] (ln_slots = N / 16: independent of the tile shape);
   //   ln_mode 2 (consumer, weights pre-multiplied by gamma): out = rstd_r * (acc - mean_r * ln_u[n]) + ln_v[n], with
   //     mean/rstd of row r from the ln_slots partials; ln_u[n] = sum_k W'[n,k], ln_v[n] = sum_k beta_k W[n,k] + bias[n].
   int ln_mode;
