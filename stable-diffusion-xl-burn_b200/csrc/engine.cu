@@ -527,6 +527,7 @@ static int build_plan_ops(sdxl_unet* u, Plan* P, Arena* A) {
   P->eps_ld = g.out_channels;
   P->eps = B.buf<float>((size_t)Bf * P->h * P->w * P->eps_ld);
   B.gn_partial = B.buf<float>(gn_scratch_floats(Bf, 32));
+  if (B.gn_partial && !A->measure && gn_scratch_init(c->stream, B.gn_partial, Bf, 32)) return fail(c, 5007, "GroupNorm scratch init failed");
   float* te = B.buf<float>(mc);
   float* t1 = B.buf<float>(ted);
   float* semb = B.buf<float>((size_t)Bf * ted);
@@ -1124,6 +1125,7 @@ extern "C" int sdxl_op_group_norm(sdxl_ctx* c, const float* x1, int C1, const fl
   if (!c || !x1 || !gamma || !beta || !out) return -1;
   TmpBufs T(c->stream);
   float* part = (float*)T.get(gn_scratch_floats(B, n_group) * 4);
+  if (part && gn_scratch_init(c->stream, part, B, n_group)) return fail(c, 5007, "GroupNorm scratch init failed");
   if (!part) return fail(c, 5330, "temporary allocation failed");
   GnParams p{x1, C1, x2, x2 ? C2 : 0, B, HW, n_group, gamma, beta, eps, silu, (__half*)out, nullptr, part, 0};
   KL(c, gn_launch(c->stream, p));

@@ -159,10 +159,12 @@ struct GnParams {
   int silu;                   // apply x*sigmoid(x) after the affine
   __half* y;                  // [B, HW, C1+C2] normalised (+SiLU) output
   __half* raw;                // nullable: un-normalised f16 copy of cat([x1,x2]) (skip-conv operand)
-  float* partial;             // scratch [B, nchunk, n_group, 2]
+  float* partial;             // scratch of gn_scratch_floats(B, n_group) floats, initialised once with gn_scratch_init
   int nchunk;                 // filled by gn_launch
 };
 size_t gn_scratch_floats(int B, int n_group);
+// zeroes the arrival counters of a freshly allocated scratch (once; the kernels leave them at zero)
+int gn_scratch_init(cudaStream_t st, float* scratch, int B, int n_group);
 int gn_launch(cudaStream_t st, GnParams& p);
 // LayerNorm over the last dim of f32 [rows, C] -> f16 [rows, C] (reference layernorm/mod.rs:34-49).
 int layernorm_launch(cudaStream_t st, const float* x, const float* gamma, const float* beta, float eps,

@@ -11,12 +11,22 @@ namespace sdxl {
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 static constexpr int kGnMaxChunk = 512;
 
-size_t gn_scratch_floats(int B, int n_group) { return (size_t)B * kGnMaxChunk * n_group * 2; }
+// scratch layout: [B][kGnMaxChunk][G][2] chunk partials | [B][G][2] final (mean, rstd) | [B] arrival counters (zero between uses)
+size_t gn_scratch_floats(int B, int n_group) { return (size_t)B * kGnMaxChunk * n_group * 2 + (size_t)B * n_group * 2 + (size_t)B + 16; }
+static inline float* gn_final(float* scratch, int B, int n_group) { return scratch + (size_t)B * kGnMaxChunk * n_group * 2; }
+static inline unsigned* gn_counters(float* scratch, int B, int n_group) { return reinterpret_cast<unsigned*>(gn_final(scratch, B, n_group) + (size_t)B * n_group * 2); }
+int gn_scratch_init(cudaStream_t st, float* scratch, int B, int n_group) {
+  return (int)cudaMemsetAsync(gn_counters(scratch, B, n_group), 0, ((size_t)B + 16) * sizeof(unsigned), st);
+}
 
-// ---- stats: grid (nchunk, B); block = V*R threads, V = C/4 float4 columns, R pixel rows in flight
+// ---- stats: grid (nchunk, B); block = V*R threads, V = C/4 float4 columns, R pixel rows in flight.
+// The last CTA of a sample to finish (arrival counter; control only, the arithmetic order is fixed) turns the chunk partials
+// into the sample's (mean, rstd) per group, so the apply kernel does not repeat that in every CTA.
 __global__ void gn_stats_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2, int HW,
-                                int n_group, int R, float* __restrict__ partial) {
+                                int n_group, int R, float eps, float* __restrict__ partial, float* __restrict__ final_stats,
+                                unsigned* __restrict__ counters) {
   extern __shared__ float sm[];  // [R][C][2]
+  __shared__ unsigned s_ticket;
   griddep_wait();
   griddep_launch_dependents();
   const int C = C1 + C2;
@@ -52,8 +62,9 @@ __global__ void gn_stats_kernel(const float* __restrict__ x1, int C1, const floa
   float* row = sm + ((size_t)rr * C + c) * 2;
   row[0] = s.x; row[1] = q.x; row[2] = s.y; row[3] = q.y; row[4] = s.z; row[5] = q.z; row[6] = s.w; row[7] = q.w;
   __syncthreads();
+  const int cpg = C / n_group;
   if (threadIdx.x < n_group) {
-    const int g = threadIdx.x, cpg = C / n_group;
+    const int g = threadIdx.x;
     float S = 0.f, Q = 0.f;
     for (int r = 0; r < R; ++r)
       for (int j = 0; j < cpg; ++j) {
@@ -64,30 +75,19 @@ __global__ void gn_stats_kernel(const float* __restrict__ x1, int C1, const floa
     float* o = partial + (((size_t)b * nchunk + chunk) * n_group + g) * 2;
     o[0] = S;
     o[1] = Q;
+    __threadfence();  // this CTA's partials are visible device-wide before it takes its ticket
   }
-}
-
-// ---- apply: grid (ctas, B); 8 channels per thread
-__global__ void gn_apply_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2, int HW,
-                                int n_group, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                float eps, int silu, const float* __restrict__ partial, int nchunk,
-                                __half* __restrict__ y, __half* __restrict__ raw) {
-  extern __shared__ float sm[];  // scale[C], shift[C], mean[G], rstd[G]
-  griddep_wait();
-  griddep_launch_dependents();
-  const int C = C1 + C2;
-  float* sc = sm;
-  float* sh = sm + C;
-  float* mean = sh + C;
-  float* rstd = mean + n_group;
-  const int b = blockIdx.y;
-  const int cpg = C / n_group;
-  // finalize the statistics: 8 lanes per group walk the chunk partials (fixed order => deterministic)
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&counters[b], 1u);
+  __syncthreads();
+  if (s_ticket != (unsigned)(nchunk - 1)) return;
+  // last CTA of sample b: 8 lanes per group walk the chunk partials in chunk order (deterministic), in double precision
+  __threadfence();
   for (int g = threadIdx.x >> 3; g < n_group; g += blockDim.x >> 3) {
     const int sub = threadIdx.x & 7;
     double S = 0.0, Q = 0.0;
     for (int k = sub; k < nchunk; k += 8) {
-      const float2 e = *reinterpret_cast<const float2*>(partial + (((size_t)b * nchunk + k) * n_group + g) * 2);
+      const float2 e = __ldcg(reinterpret_cast<const float2*>(partial + (((size_t)b * nchunk + k) * n_group + g) * 2));
       S += (double)e.x;
       Q += (double)e.y;
     }
@@ -101,58 +101,56 @@ __global__ void gn_apply_kernel(const float* __restrict__ x1, int C1, const floa
       const double m = S / n;
       double var = Q / n - m * m;
       if (var < 0.0) var = 0.0;
-      mean[g] = (float)m;
-      rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+      final_stats[((size_t)b * n_group + g) * 2] = (float)m;
+      final_stats[((size_t)b * n_group + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
     }
   }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
-    const float s = rstd[g] * gamma[c];
-    sc[c] = s;
-    sh[c] = beta[c] - mean[g] * s;
-  }
-  __syncthreads();
+  if (threadIdx.x == 0) counters[b] = 0u;  // ready for the next GroupNorm that uses this scratch
+}
+
+// ---- apply: grid (ctas, B); block = V8*R threads: a thread owns 8 fixed channels (scale/shift in registers) and walks
+// pixel rows, no index divisions in the loop
+__global__ void gn_apply_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2, int HW,
+                                int n_group, const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
+                                const float* __restrict__ final_stats, int R, __half* __restrict__ y, __half* __restrict__ raw) {
+  griddep_wait();
+  griddep_launch_dependents();
+  const int C = C1 + C2;
   const int V8 = C >> 3;
-  const long total = (long)HW * V8;
-  const long stride = (long)gridDim.x * blockDim.x;
-  for (long idx0 = (long)blockIdx.x * blockDim.x + threadIdx.x; idx0 < total; idx0 += 2 * stride) {
-    // two independent items per trip: both 32 B loads are issued before either is consumed
-    float4 la[2][2];
-    const float* srcs[2];
+  const int v = threadIdx.x % V8, rr = threadIdx.x / V8;
+  if (rr >= R) return;
+  const int b = blockIdx.y;
+  const int cpg = C / n_group;
+  const int c = v * 8;
+  float sc[8], sh[8];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const long idx = idx0 + u * stride;
-      if (idx < total) {
-        const int v = (int)(idx % V8);
-        const long p = idx / V8;
-        const int c = v * 8;
-        srcs[u] = (c < C1) ? x1 + ((size_t)b * HW + p) * C1 + c : x2 + ((size_t)b * HW + p) * C2 + (c - C1);
-        la[u][0] = *reinterpret_cast<const float4*>(srcs[u]);
-        la[u][1] = *reinterpret_cast<const float4*>(srcs[u] + 4);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-    const long idx = idx0 + u * stride;
-    if (idx >= total) continue;
-    const int v = (int)(idx % V8);
-    const long p = idx / V8;
-    const int c = v * 8;
-    const float4 a0 = la[u][0], a1 = la[u][1];
+  for (int i = 0; i < 8; ++i) {
+    const int g = (c + i) / cpg;
+    const float mean = final_stats[((size_t)b * n_group + g) * 2], rstd = final_stats[((size_t)b * n_group + g) * 2 + 1];
+    sc[i] = rstd * gamma[c + i];
+    sh[i] = beta[c + i] - mean * sc[i];
+  }
+  const float* src;
+  int cc, Cs;
+  if (c < C1) { src = x1; cc = c; Cs = C1; } else { src = x2; cc = c - C1; Cs = C2; }
+  src += (size_t)b * HW * Cs + cc;
+  __half* yo = y + (size_t)b * HW * C + c;
+  __half* ro = raw ? raw + (size_t)b * HW * C + c : nullptr;
+  const int step = gridDim.x * R;
+  auto emit = [&](int p, const float4& a0, const float4& a1) {
     float f[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
     uint32_t h[4];
-    if (raw) {
+    if (ro) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         __half2 t = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
         h[i] = *reinterpret_cast<uint32_t*>(&t);
       }
-      *reinterpret_cast<uint4*>(raw + ((size_t)b * HW + p) * C + c) = make_uint4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<uint4*>(ro + (size_t)p * C) = make_uint4(h[0], h[1], h[2], h[3]);
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      float t = fmaf(f[i], sc[c + i], sh[c + i]);
+      float t = fmaf(f[i], sc[i], sh[i]);
       if (silu) t = silu_f(t);
       f[i] = t;
     }
@@ -161,8 +159,23 @@ __global__ void gn_apply_kernel(const float* __restrict__ x1, int C1, const floa
       __half2 t = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
       h[i] = *reinterpret_cast<uint32_t*>(&t);
     }
-    *reinterpret_cast<uint4*>(y + ((size_t)b * HW + p) * C + c) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(yo + (size_t)p * C) = make_uint4(h[0], h[1], h[2], h[3]);
+  };
+  int p = blockIdx.x * R + rr;
+  for (; p + 3 * step < HW; p += 4 * step) {  // four rows (eight 16-byte loads) in flight per thread
+    float4 a[4][2];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float* s = src + (size_t)(p + u * step) * Cs;
+      a[u][0] = *reinterpret_cast<const float4*>(s);
+      a[u][1] = *reinterpret_cast<const float4*>(s + 4);
     }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) emit(p + u * step, a[u][0], a[u][1]);
+  }
+  for (; p < HW; p += step) {
+    const float* s = src + (size_t)p * Cs;
+    emit(p, *reinterpret_cast<const float4*>(s), *reinterpret_cast<const float4*>(s + 4));
   }
 }
 
@@ -186,16 +199,21 @@ int gn_launch(cudaStream_t st, GnParams& p) {
     cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     attr = true;
   }
+  float* fin = gn_final(p.partial, p.B, p.n_group);
+  unsigned* cnt = gn_counters(p.partial, p.B, p.n_group);
   int e = launch_kernel(gn_stats_kernel, dim3(nchunk, p.B), dim3(V * R), smem1, st, true, p.x1, p.C1, p.x2, p.C2, p.HW,
-                        p.n_group, R, p.partial);
+                        p.n_group, R, p.eps, p.partial, fin, cnt);
   if (e) return e;
-  const size_t smem2 = (size_t)(2 * C + 2 * p.n_group) * sizeof(float);
-  int ctas = cdiv((long)p.HW * (C / 8), 256 * 4);
+  const int V8 = C / 8;
+  int R2 = 256 / V8;
+  if (R2 < 1) R2 = 1;
+  if (R2 > 32) R2 = 32;
+  int ctas = cdiv(p.HW, R2 * 4);
   const int cap = (148 * 8) / (p.B > 0 ? p.B : 1);
   if (ctas > cap) ctas = cap;
   if (ctas < 1) ctas = 1;
-  return launch_kernel(gn_apply_kernel, dim3(ctas, p.B), dim3(256), smem2, st, true, p.x1, p.C1, p.x2, p.C2, p.HW,
-                       p.n_group, p.gamma, p.beta, p.eps, p.silu, (const float*)p.partial, nchunk, p.y, p.raw);
+  return launch_kernel(gn_apply_kernel, dim3(ctas, p.B), dim3(V8 * R2), (size_t)0, st, true, p.x1, p.C1, p.x2, p.C2, p.HW,
+                       p.n_group, p.gamma, p.beta, p.silu, (const float*)fin, R2, p.y, p.raw);
 }
 
 // ------------------------------------------------------------------------------------------------

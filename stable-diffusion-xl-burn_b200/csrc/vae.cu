@@ -369,6 +369,7 @@ static int build_vae_plan(sdxl_vae* v, Plan* P, Arena* A) {
   P->x_in = B.buf<float>((size_t)Bn * Cl * st.H * st.W);
   float* pq_out = B.buf<float>((size_t)Bn * Cl * st.H * st.W);
   B.gn_partial = B.buf<float>(gn_scratch_floats(Bn, 32));
+  if (B.gn_partial && !A->measure && gn_scratch_init(c->stream, B.gn_partial, Bn, 32)) return fail(c, 5007, "GroupNorm scratch init failed");
   st.alloc(max_x, max_in, max_out, st.H * st.W, v->C0);
   __half* s_up = max_up ? B.buf<__half>(Bn * max_up) : nullptr;
   if (B.err) return B.err;
@@ -454,6 +455,7 @@ static int build_vae_enc_plan(sdxl_vae* v, Plan* P, Arena* A) {
   P->x_in = B.buf<float>((size_t)Bn * 3 * st.H * st.W);
   v->enc_u8 = B.buf<uint8_t>((size_t)Bn * 3 * st.H * st.W);
   B.gn_partial = B.buf<float>(gn_scratch_floats(Bn, 32));
+  if (B.gn_partial && !A->measure && gn_scratch_init(c->stream, B.gn_partial, Bn, 32)) return fail(c, 5007, "GroupNorm scratch init failed");
   st.alloc(max_x, max_in, max_out, hl * wl, Ce);
   __half* s_ph = max_ph ? B.buf<__half>(Bn * max_ph) : nullptr;
   v->enc_z = B.buf<float>((size_t)Bn * hl * wl * Cz);
