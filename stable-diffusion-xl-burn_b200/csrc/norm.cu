@@ -86,10 +86,16 @@ __global__ void gn_stats_kernel(const float* __restrict__ x1, int C1, const floa
   for (int g = threadIdx.x >> 3; g < n_group; g += blockDim.x >> 3) {
     const int sub = threadIdx.x & 7;
     double S = 0.0, Q = 0.0;
-    for (int k = sub; k < nchunk; k += 8) {
-      const float2 e = __ldcg(reinterpret_cast<const float2*>(partial + (((size_t)b * nchunk + k) * n_group + g) * 2));
-      S += (double)e.x;
-      Q += (double)e.y;
+    for (int k0 = sub; k0 < nchunk; k0 += 64) {   // eight independent loads in flight, summed in chunk order
+      float2 e[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = k0 + 8 * j;
+        e[j] = k < nchunk ? __ldcg(reinterpret_cast<const float2*>(partial + (((size_t)b * nchunk + k) * n_group + g) * 2))
+                          : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { S += (double)e[j].x; Q += (double)e[j].y; }
     }
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) {
