@@ -72,3 +72,24 @@ def test_block_program_base():
                                                  (960, 320), (640, 320), (640, 320)]
     assert mid.depth == 10 and mid.n_head == 20
     assert [b.kind for b in ins].count("downsample") == 2
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """A C99 program including include/sdxl_b200.h compiles with gcc, links against libsdxl_b200.so (every referenced entry
+    point resolves) and drives the CPU-only tokenizer entry points — the binding a cgo / Rust `extern "C"` shim would make."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    lib_dir = os.path.join(root, "stable-diffusion-xl-burn_b200", "sdxl_b200")
+    exe = str(tmp_path / "abi_check")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(root, "include"),
+                        os.path.join(root, "tests", "c_abi", "abi_check.c"), "-L", lib_dir, "-lsdxl_b200", "-Wl,-rpath," + lib_dir, "-o", exe],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    mini = os.path.join(root, "tests", "golden", "mini_bpe")
+    r = subprocess.run([exe, os.path.join(mini, "merges.txt"), os.path.join(mini, "vocab.txt")], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert r.stdout.startswith("abi_check ok")
