@@ -315,7 +315,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         "bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
         # dram__bytes_read+write of the largest igemm launch (FF-in GEGLU, M=2048 N=10240 K=1280; algorithmic bytes
         # 26.2 MB weights + 5.2 MB activations in + 21 MB out) from the ncu --set full capture profiles/r1k_ncu_full_igemm.csv
-        "traffic": 32.45e6, "traffic_unit": "bytes/launch (ncu, FF-in GEGLU launch; writes stay in L2)",
+        "traffic": 32.60e6, "traffic_unit": "bytes/launch (ncu --set full, profiles/r1final_ncu_full_igemm.csv: FF-in GEGLU launch, 31.56 MB read + 1.03 MB written; algorithmic operand bytes 31.4 MB)",
         "kernel": "igemm_kernel (tcgen05 implicit GEMM: all Linear + conv of the step)",
         "peak_source": peaks["src"],
         "how": "sum of algorithmic FLOPs of the step's igemm launches / sum of their CUDA-event durations (eager replay of the same plan on the ctx stream)",
