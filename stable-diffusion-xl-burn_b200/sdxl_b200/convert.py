@@ -94,3 +94,26 @@ def write_npy_tree(weights: Dict[str, torch.Tensor], root: str, alphas_root: Opt
             write_tensor(alphas_root if alphas_root is not None else os.path.dirname(os.path.abspath(root)), name, t)
         else:
             write_tensor(root, name, t)
+
+
+def _main(argv=None) -> int:
+    """`python -m sdxl_b200.convert <model> <npy tree root> <out.pack>` — the role of the reference's `convert` binary
+    (src/bin/convert/main.rs) for this library's pack format. model: unet_base | unet_refiner | vae | clip_l | open_clip_g."""
+    import argparse
+    from .config import SDXL_BASE, SDXL_CLIP_L, SDXL_OPEN_CLIP_G, SDXL_REFINER, SDXL_VAE
+    models = {"unet_base": SDXL_BASE, "unet_refiner": SDXL_REFINER, "vae": SDXL_VAE, "clip_l": SDXL_CLIP_L, "open_clip_g": SDXL_OPEN_CLIP_G}
+    ap = argparse.ArgumentParser(prog="python -m sdxl_b200.convert", description=_main.__doc__)
+    ap.add_argument("model", choices=sorted(models))
+    ap.add_argument("root", help="directory of the npy dump tree for this model (e.g. params/diffuser_base)")
+    ap.add_argument("out", help="output pack file")
+    ap.add_argument("--alphas-root", default=None, help="directory holding alphas_cumprod.npy (UNet only; default: parent of root)")
+    a = ap.parse_args(argv)
+    pack = pack_from_npy_tree(a.root, models[a.model], a.alphas_root)
+    with open(a.out, "wb") as f:
+        f.write(pack.numpy().tobytes())
+    print(f"wrote {a.out}: {pack.numel()} bytes")
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(_main())

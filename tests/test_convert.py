@@ -44,3 +44,14 @@ def test_errors(tmp_path):
     np.save(os.path.join(root, "decoder", "conv_in", "bias.npy"), np.array([5.0, 1.0, 2.0], dtype=np.float32))
     with pytest.raises(NpyTreeError, match="shape prefix"):
         load_npy_tree(root, TINY_VAE)
+
+
+def test_convert_cli_writes_the_same_pack(tmp_path, monkeypatch):
+    from sdxl_b200 import convert, config
+    monkeypatch.setattr(config, "SDXL_VAE", TINY_VAE)   # the CLI's model table, shrunk for the test
+    w = synth_weights(TINY_VAE, seed=3)
+    root = str(tmp_path / "vae")
+    write_npy_tree(w, root)
+    out = str(tmp_path / "vae.pack")
+    assert convert._main(["vae", root, out]) == 0
+    assert open(out, "rb").read() == build_pack(w).numpy().tobytes()

@@ -158,3 +158,18 @@ def test_errors_are_reported_not_thrown_across_the_abi():
     # a merges file that is too short for ClipTokenizer::new's hard-coded slice (clip.rs:98)
     with pytest.raises(SdxlError, match="needs"):
         ClipTokenizer(os.path.join(MINI, "merges.txt"))
+
+
+def test_invalid_utf8_is_replaced_like_from_utf8_lossy(mini):
+    """The C ABI takes bytes: malformed UTF-8 decodes with U+FFFD per maximal invalid subpart (String::from_utf8_lossy, which a
+    Rust caller converting from raw bytes would have applied) — same ids as the oracle on bytes.decode(errors="replace")."""
+    import ctypes as C
+    from sdxl_b200 import _lib
+    tok, oracle = mini
+    lib = _lib.load()
+    for raw in (b"caf\xc3 au lait", b"\xff\xfe cat", b"x\xe2\x82 y", b"\xf0\x9f\x98 smile", b"ok \xed\xa0\x80 surrogate", b"\xc0\xaf overlong"):
+        n = C.c_int(0)
+        assert lib.sdxl_tokenizer_encode(tok.h, raw, 0, 0, None, 0, C.byref(n)) == 0
+        buf = (C.c_uint32 * max(1, n.value))()
+        assert lib.sdxl_tokenizer_encode(tok.h, raw, 0, 0, buf, n.value, C.byref(n)) == 0
+        assert list(buf[:n.value]) == oracle.encode(raw.decode("utf-8", errors="replace"), False, False), raw
