@@ -67,3 +67,46 @@ def test_clip_golden_reproduces():
     assert np.allclose(h1.numpy(), g["hidden_clip"], atol=2e-5, rtol=1e-5)
     assert np.allclose(h2.numpy(), g["hidden_open_clip"], atol=2e-5, rtol=1e-5)
     assert np.allclose(p2.numpy(), g["pooled_open_clip"], atol=2e-5, rtol=1e-5)
+
+
+def _hf_text_model(cfg, w):
+    """The same weights loaded into HuggingFace transformers' CLIPTextModelWithProjection (an independent implementation of the
+    architecture the reference's dump scripts port from); Linear weights are [in, out] in the dump tree, [out, in] in PyTorch."""
+    transformers = __import__("pytest").importorskip("transformers")
+    hc = transformers.CLIPTextConfig(vocab_size=cfg.n_vocab, hidden_size=cfg.n_state, intermediate_size=4 * cfg.n_state,
+                                     num_hidden_layers=cfg.n_layer, num_attention_heads=cfg.n_head, max_position_embeddings=cfg.n_ctx,
+                                     hidden_act="quick_gelu" if cfg.quick_gelu else "gelu", projection_dim=cfg.embed_dim,
+                                     eos_token_id=49407, bos_token_id=49406, pad_token_id=0, layer_norm_eps=1e-5, attention_dropout=0.0)
+    m = transformers.CLIPTextModelWithProjection(hc).eval()
+    sd = {"text_model.embeddings.token_embedding.weight": w["token_embedding/weight"],
+          "text_model.embeddings.position_embedding.weight": w["position_embedding/weight"],
+          "text_model.final_layer_norm.weight": w["layer_norm/weight"], "text_model.final_layer_norm.bias": w["layer_norm/bias"],
+          "text_projection.weight": w["text_projection"].t().contiguous()}
+    for i in range(cfg.n_layer):
+        b, h = f"blocks/{i}", f"text_model.encoder.layers.{i}"
+        for ours, theirs in (("attn/query", "self_attn.q_proj"), ("attn/key", "self_attn.k_proj"), ("attn/value", "self_attn.v_proj"),
+                             ("attn/out", "self_attn.out_proj"), ("mlp/fc1", "mlp.fc1"), ("mlp/fc2", "mlp.fc2")):
+            sd[f"{h}.{theirs}.weight"] = w[f"{b}/{ours}/weight"].t().contiguous()
+            sd[f"{h}.{theirs}.bias"] = w[f"{b}/{ours}/bias"]
+        for ours, theirs in (("attn_ln", "layer_norm1"), ("mlp_ln", "layer_norm2")):
+            sd[f"{h}.{theirs}.weight"] = w[f"{b}/{ours}/weight"]
+            sd[f"{h}.{theirs}.bias"] = w[f"{b}/{ours}/bias"]
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all("position_ids" in k for k in missing), (missing, unexpected)
+    return m
+
+
+def test_oracle_vs_huggingface_clip_text_model():
+    """Pins the text-encoder oracle against HuggingFace transformers' CLIP text tower on the same weights: the stream entering
+    the last block (== hidden_states[n_layer-1], SDXL's "penultimate layer") and the projected end-of-text feature."""
+    for cfg, seed, pad in ((TINY_CLIP, 1, 49407), (TINY_OPEN_CLIP, 2, 0)):
+        w = O.to_f32(synth_weights(cfg, seed=seed))
+        m = _hf_text_model(cfg, w)
+        rows = [[49406, 320, 1125, 539, 320, 2368, 49407], [49406, 17, 4, 256, 300, 301, 302, 303, 9, 49407]]
+        tok = torch.tensor([r + [pad] * (77 - len(r)) for r in rows])
+        with torch.no_grad():
+            out = m(input_ids=tok, output_hidden_states=True)
+        h, pooled = CO.forward_hidden_pooled(cfg, w, tok, cfg.n_layer - 1)
+        assert torch.allclose(h, out.hidden_states[cfg.n_layer - 1], atol=5e-5, rtol=1e-4)
+        assert torch.allclose(CO.forward_hidden(cfg, w, tok, 1), out.hidden_states[1], atol=5e-5, rtol=1e-4)
+        assert torch.allclose(pooled, out.text_embeds, atol=1e-4, rtol=1e-4)

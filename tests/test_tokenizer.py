@@ -173,3 +173,21 @@ def test_invalid_utf8_is_replaced_like_from_utf8_lossy(mini):
         buf = (C.c_uint32 * max(1, n.value))()
         assert lib.sdxl_tokenizer_encode(tok.h, raw, 0, 0, buf, n.value, C.byref(n)) == 0
         assert list(buf[:n.value]) == oracle.encode(raw.decode("utf-8", errors="replace"), False, False), raw
+
+
+@need_ref
+def test_open_clip_ids_match_huggingface_tokenizers(real):
+    """Independent check: the HuggingFace `tokenizers` runtime on the reference's own tokenizer.json (the file its
+    vocab.txt / merges.txt were exported from, tokenizer/convert.py) gives the same ids as the oracle and the C++ tokenizer
+    (NFC-stable prompts: tokenizer.json normalises with NFC, the reference's Rust code does not)."""
+    tk = pytest.importorskip("tokenizers")
+    path = os.path.join(REF_TOK, "tokenizer.json")
+    if not os.path.exists(path):
+        pytest.skip("tokenizer.json not present")
+    hf = tk.Tokenizer.from_file(path)
+    tok, oracle = real["open_clip"]
+    for p in ["a photo of a cat", "An astronaut riding a horse on Mars, 4k, highly-detailed!!",
+              "it's the artist's 1st painting; they've said we'll see", "Ünïcödé façade naïve café", "x²+y³ = 42 %"]:
+        want = hf.encode(p).ids            # adds <|startoftext|> / <|endoftext|>
+        assert oracle.encode(p, True, True) == want, p
+        assert tok.encode(p, True, True) == want, p
