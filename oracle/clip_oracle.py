@@ -10,7 +10,8 @@ src/model/stablediffusion/mod.rs:654-776 (Embedder::text_to_conditioning and hel
 tests/test_clip_oracle.py cross-checks the block against torch.nn.functional primitives (F.layer_norm,
 F.scaled_dot_product_attention(is_causal=True), F.gelu) and the whole encoder against HuggingFace transformers'
 CLIPTextModelWithProjection loaded with the same weights (hidden_states[n_layer-1] and text_embeds agree to 1e-4): the
-architecture is pinned against its canonical implementation, the reference's Rust port of it is what stays unverifiable.
+architecture is pinned against its canonical implementation — the very model the reference's dump script reads its CLIP-L
+weights from (python/clip.py:7-48 walks a HuggingFace CLIPTextModel); the reference's Rust port of it is what stays unverifiable.
 """
 from __future__ import annotations
 
