@@ -3,6 +3,8 @@
 // warp shuffles + a small deterministic partial-sum table (no atomics).
 //   reference: groupnorm/mod.rs:52-82 (reshape to [B,32,C/32*HW], biased variance, eps inside sqrt,
 //   per-channel affine), layernorm/mod.rs:34-49, silu.rs:14-16.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -279,7 +281,8 @@ int layernorm_launch(cudaStream_t st, const float* x, const float* gamma, const 
                      int C, __half* y) {
   if (C & 3) return 3003;
   const int nv = cdiv(C, 128);
-  const int warps = 8;
+  static const int warps_env = getenv("SDXL_B200_LN_WARPS") ? atoi(getenv("SDXL_B200_LN_WARPS")) : 0;
+  const int warps = (warps_env >= 1 && warps_env <= 32) ? warps_env : 8;
   dim3 grid(cdiv(rows, warps));
   if (nv <= 1) return launch_kernel(layernorm_kernel<1>, grid, dim3(warps * 32), (size_t)0, st, true, x, gamma, beta, eps, rows, C, y);
   else if (nv <= 2) return launch_kernel(layernorm_kernel<2>, grid, dim3(warps * 32), (size_t)0, st, true, x, gamma, beta, eps, rows, C, y);
