@@ -1,7 +1,7 @@
 """Generates the tokenizer fixtures from the ORACLE (oracle/tokenizer_oracle.py — pinned by the reference's own
 known-answer vector, see its header):
 
-  tests/golden/mini_bpe/{merges.txt,vocab.txt}   a small synthetic BPE vocabulary (trained here on PROMPTS with a plain
+  tests/golden/mini_bpe/{mini_merges.txt,mini_vocab.txt}   a small synthetic BPE vocabulary (trained here on PROMPTS with a plain
                                                  most-frequent-pair loop) so the C++ tokenizer can be tested on machines that do
                                                  not have the reference's vocabulary files (the GPU box);
   tests/golden/tokenizer_vectors.json            prompt -> ids for (a) the mini vocabulary, (b) the reference's real CLIP and
@@ -85,15 +85,15 @@ def main():
     vocab += ["<|startoftext|>", "<|endoftext|>"]
     # ids 49406 / 49407 are hard-coded in the reference (clip.rs:215-221); the mini vocabulary is smaller, so sot/eot ids
     # simply do not decode — encode() never looks them up.
-    with open(os.path.join(mini, "merges.txt"), "w", encoding="utf-8", newline="\n") as f:
+    with open(os.path.join(mini, "mini_merges.txt"), "w", encoding="utf-8", newline="\n") as f:
         f.write("#version:mini\n")  # a one-word line: load_merges skips it
         for a, b in merges:
             f.write(f"{a} {b}\n")
-    with open(os.path.join(mini, "vocab.txt"), "w", encoding="utf-8", newline="\n") as f:
+    with open(os.path.join(mini, "mini_vocab.txt"), "w", encoding="utf-8", newline="\n") as f:
         for v in vocab:
             f.write(v + "\n")
     out = {"prompts": PROMPTS, "mini": {}, "clip": {}, "open_clip": {}}
-    tok = T.OpenClipTokenizer(os.path.join(mini, "merges.txt"), os.path.join(mini, "vocab.txt"))
+    tok = T.OpenClipTokenizer(os.path.join(mini, "mini_merges.txt"), os.path.join(mini, "mini_vocab.txt"))
     out["mini"]["encode"] = [tok.encode(p, False, False) for p in PROMPTS]
     out["mini"]["tokenize_text_77"] = [T.tokenize_text(p, tok, 77) for p in PROMPTS]
     out["mini"]["decode"] = [tok.decode(e) for e in out["mini"]["encode"]]

@@ -91,8 +91,8 @@ def test_masked_qkv_attention_op(ctx):
 def test_embedder_text_to_conditioning(ctx, enc):
     """End to end: text -> tokenizers -> encoders -> Conditioning, then one UNet forward consumes it."""
     e1, e2, w1, w2 = enc
-    tok = OpenClipTokenizer(os.path.join(MINI, "merges.txt"), os.path.join(MINI, "vocab.txt"))
-    otok = TO.OpenClipTokenizer(os.path.join(MINI, "merges.txt"), os.path.join(MINI, "vocab.txt"))
+    tok = OpenClipTokenizer(os.path.join(MINI, "mini_merges.txt"), os.path.join(MINI, "mini_vocab.txt"))
+    otok = TO.OpenClipTokenizer(os.path.join(MINI, "mini_merges.txt"), os.path.join(MINI, "mini_vocab.txt"))
     emb = Embedder(ctx, e1, e2, tok, tok)
     text = "An astronaut riding a horse on Mars, 4k"
     size, crop, ar = (1024, 1024), (0, 0), (1024, 1024)

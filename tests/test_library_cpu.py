@@ -90,6 +90,6 @@ def test_header_is_plain_c_and_links(tmp_path):
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     mini = os.path.join(root, "tests", "golden", "mini_bpe")
-    r = subprocess.run([exe, os.path.join(mini, "merges.txt"), os.path.join(mini, "vocab.txt")], capture_output=True, text=True, timeout=60)
+    r = subprocess.run([exe, os.path.join(mini, "mini_merges.txt"), os.path.join(mini, "mini_vocab.txt")], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
     assert r.stdout.startswith("abi_check ok")

@@ -33,7 +33,7 @@ def rel_err(a, b):
 def test_text_to_image_and_inpaint(ctx):
     wa, wb, wu, wv = (synth_weights(c, seed=s) for c, s in ((CLIP_A, 1), (CLIP_B, 2), (UNET, 3), (TINY_VAE, 0)))
     ea, eb = ClipTextEncoder(ctx, CLIP_A, wa), ClipTextEncoder(ctx, CLIP_B, wb)
-    tok = OpenClipTokenizer(os.path.join(MINI, "merges.txt"), os.path.join(MINI, "vocab.txt"))
+    tok = OpenClipTokenizer(os.path.join(MINI, "mini_merges.txt"), os.path.join(MINI, "mini_vocab.txt"))
     emb = Embedder(ctx, ea, eb, tok, tok)
     dif = Diffuser(ctx, UNET, wu)
     vae = LatentDecoder(ctx, TINY_VAE, wv)
@@ -46,7 +46,7 @@ def test_text_to_image_and_inpaint(ctx):
     assert rgb.shape == (1, 32, 32, 3) and rgb.dtype == torch.uint8
 
     # oracle chain on the same inputs
-    otok = TO.OpenClipTokenizer(os.path.join(MINI, "merges.txt"), os.path.join(MINI, "vocab.txt"))
+    otok = TO.OpenClipTokenizer(os.path.join(MINI, "mini_merges.txt"), os.path.join(MINI, "mini_vocab.txt"))
     oc = CO.text_to_conditioning(CLIP_A, O.to_f32(wa), CLIP_B, O.to_f32(wb), otok, otok, TO.tokenize_text, text, res, (0, 0), res)
     h16 = lambda t: t.to(torch.float16).float()  # Conditioning::convert
     ocond = O.OracleConditioning(context_full=h16(oc["context_full"]), unconditional_context_full=h16(oc["unconditional_context_full"]),

@@ -30,8 +30,8 @@ KAT_DECODE = "hello world ! <|startoftext|>asdf <|startoftext|>"
 
 @pytest.fixture(scope="module")
 def mini():
-    return (OpenClipTokenizer(os.path.join(MINI, "merges.txt"), os.path.join(MINI, "vocab.txt")),
-            TO.OpenClipTokenizer(os.path.join(MINI, "merges.txt"), os.path.join(MINI, "vocab.txt")))
+    return (OpenClipTokenizer(os.path.join(MINI, "mini_merges.txt"), os.path.join(MINI, "mini_vocab.txt")),
+            TO.OpenClipTokenizer(os.path.join(MINI, "mini_merges.txt"), os.path.join(MINI, "mini_vocab.txt")))
 
 
 @pytest.fixture(scope="module")
@@ -157,7 +157,7 @@ def test_errors_are_reported_not_thrown_across_the_abi():
         ClipTokenizer("/nonexistent/bpe.txt")
     # a merges file that is too short for ClipTokenizer::new's hard-coded slice (clip.rs:98)
     with pytest.raises(SdxlError, match="needs"):
-        ClipTokenizer(os.path.join(MINI, "merges.txt"))
+        ClipTokenizer(os.path.join(MINI, "mini_merges.txt"))
 
 
 def test_invalid_utf8_is_replaced_like_from_utf8_lossy(mini):
