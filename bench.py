@@ -206,16 +206,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     ctx = sdxl_b200.Context(local_rank)
     # weights: rank 0 generates the pack on its GPU, one NCCL broadcast, every rank re-lays it out locally
     t0 = time.perf_counter()
-    if rank == 0:
-        pack = sdxl_b200.build_pack(sdxl_b200.synth_weights(cfg, seed=0, device=str(dev)))
-        nbytes = torch.tensor([pack.numel()], device=dev, dtype=torch.int64)
-    else:
-        nbytes = torch.zeros(1, device=dev, dtype=torch.int64)
-    if world > 1:
-        dist.broadcast(nbytes, 0)
-        if rank != 0:
-            pack = torch.empty(int(nbytes.item()), dtype=torch.uint8, device=dev)
-        dist.broadcast(pack, 0)
+    from sdxl_b200 import sharding
+    pack = sdxl_b200.build_pack(sdxl_b200.synth_weights(cfg, seed=0, device=str(dev))) if rank == 0 else None
+    pack = sharding.broadcast_pack(pack, 0, dev)   # one flat NCCL message (world 1: returned as is)
     torch.cuda.synchronize()
     diffuser = sdxl_b200.Diffuser(ctx, cfg, pack)
     ctx.synchronize()
@@ -271,10 +264,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     clocks = sampler.stop()
     ms_total = e0.elapsed_time(e1)
     launches = ctx.launch_count - launches0
-    t_ms = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_step = float(t_ms.item()) / args.steps
+    ms_step = sharding.max_over_ranks(ms_total, dev) / args.steps   # timing rule: max over ranks of the device time
     value = world * 1e3 / ms_step
 
     # ---- e2e: same step through the host-buffer entry point (H2D latent in, D2H latent out, every step) ----
@@ -290,10 +280,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         if not torch.isfinite(host_lat).all():
             host_lat.normal_()
     torch.cuda.synchronize()
-    e2e_ms = torch.tensor([(time.perf_counter() - w0) * 1e3 / e2e_steps], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = world * 1e3 / float(e2e_ms.item())
+    e2e_ms = sharding.max_over_ranks((time.perf_counter() - w0) * 1e3 / e2e_steps, dev)
+    e2e_value = world * 1e3 / e2e_ms
 
     if rank != 0:
         if world > 1:
