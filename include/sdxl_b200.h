@@ -40,6 +40,7 @@ typedef struct sdxl_ctx sdxl_ctx;
 typedef struct sdxl_unet sdxl_unet;
 
 #define SDXL_MAX_LEVELS 8
+#define SDXL_PROFILE_KINDS 24   /* entries of the per-kernel-kind arrays of the *_profile_plan entry points */
 
 /* Mirrors DiffuserConfig (src/model/stablediffusion/mod.rs:269-278) + UNetConfig
  * (src/model/unet/mod.rs:59-69). Transformer blocks exist on levels 1 and 2 only
@@ -148,7 +149,7 @@ SDXL_API int sdxl_unet_plan_num_ops(const sdxl_unet* unet);
 /* Device time of ONE execution of the current launch plan, summed per kernel kind and measured with CUDA
  * events on the ctx stream (eager launches). Kind index: 0 implicit-GEMM (tcgen05), 1 attention, 2 GroupNorm,
  * 3 LayerNorm, 4 GEMV, 5 timestep-embedding, 6 first conv, 7 upsample copy, 8 phase-split copy, 9 f32->f16 cast.
- * All three arrays hold 16 entries (host). Used by bench.py for the per-kernel roofline. */
+ * All three arrays hold SDXL_PROFILE_KINDS entries (host). Used by bench.py for the per-kernel roofline. */
 SDXL_API int sdxl_unet_profile_plan(sdxl_unet* unet, double* ms_by_kind_host, double* flops_by_kind_host,
                                     int* launches_by_kind_host);
 /* Same measurement, one CSV row per launch (analysis aid; written to `path_host`). */
@@ -157,6 +158,9 @@ SDXL_API int sdxl_unet_profile_dump(sdxl_unet* unet, const char* path_host);
  * [M,K]x[K,N] problem; stamps_host[9]: see csrc/engine.cu. */
 SDXL_API int sdxl_dbg_igemm_timeline(sdxl_ctx* ctx, int M, int K, int N, int geglu, int with_residual,
                                      uint64_t* stamps_host);
+/* Diagnostics: attention kernel variant = fraction of the softmax exponentials evaluated on the FMA pipe instead of
+ * the MUFU (0 none, 1 a quarter, 2 half; -1 = default). Process-wide. */
+SDXL_API void sdxl_dbg_attention_variant(int poly);
 /* seeded N(0,1) exactly as the sampler generates it (device out). */
 SDXL_API int sdxl_randn(sdxl_ctx* ctx, float* out, size_t n, uint64_t seed, uint64_t subsequence);
 

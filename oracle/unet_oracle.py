@@ -298,8 +298,9 @@ def get_alpha(alphas: torch.Tensor, i: int) -> float:
 
 def diffuse_latent(cfg, w: W, alphas: torch.Tensor, latent: torch.Tensor, c: OracleConditioning, step_start: int, n_steps: int,
                    guidance: float, reference: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None,
-                   step_noise: Optional[Sequence[torch.Tensor]] = None) -> torch.Tensor:
-    """Diffuser::diffuse_latent (:390-432) and diffuse_latent_with_inpainting (:434-483); DDIM, sigma = 0."""
+                   step_noise: Optional[Sequence[torch.Tensor]] = None, trace=None) -> torch.Tensor:
+    """Diffuser::diffuse_latent (:390-432) and diffuse_latent_with_inpainting (:434-483); DDIM, sigma = 0.
+    `trace(iteration, latent)` (test aid, not in the reference) is called after every loop iteration."""
     total = cfg.n_steps
     step_size = total // n_steps                                # :400
     start = total - step_start                                  # :404
@@ -317,12 +318,14 @@ def diffuse_latent(cfg, w: W, alphas: torch.Tensor, latent: torch.Tensor, c: Ora
         dir_latent = pred_noise * math.sqrt(1.0 - prev_alpha)                      # :424
         latent = predx0 * math.sqrt(prev_alpha) + dir_latent                       # :426-428 (sigma = 0)
         it += 1
+        if trace is not None:
+            trace(it, latent)
     return latent
 
 
-def sample_latent(cfg, w, alphas, noise, c, guidance, n_steps):
+def sample_latent(cfg, w, alphas, noise, c, guidance, n_steps, trace=None):
     """Diffuser::sample_latent, :317-332 (noise = gen_noise(), injected)."""
-    return diffuse_latent(cfg, w, alphas, noise, c, 0, n_steps, guidance)
+    return diffuse_latent(cfg, w, alphas, noise, c, 0, n_steps, guidance, trace=trace)
 
 
 def sample_latent_with_inpainting(cfg, w, alphas, noise, c, guidance, n_steps, reference, mask, step_noise):

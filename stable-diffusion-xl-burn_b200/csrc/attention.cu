@@ -1,16 +1,22 @@
 // Fused multi-head attention for the UNet's SpatialTransformer blocks (head dim 64, no mask):
 //   out = softmax(q k^T / sqrt(64)) v            (reference src/backend.rs:4-19,32-79,88-128;
 //                                                 called from unet/mod.rs:1013-1019)
-// Flash-style on tcgen05 tensor cores with TMEM accumulators. One CTA owns TWO 128-query tiles (A, B) of one
-// head and streams 128-key blocks once for both; two softmax warpgroups ping-pong against one MMA issuer, so
-// the tensor pipe works on tile B while tile A is in the exp/rescale phase and vice versa:
-//   S_x = Q_x K^T : A = Q tile (K-major, TMA SW128), B = K tile (K-major)            -> TMEM S_A / S_B (128 cols each)
-//   O_x,j = P_x V : A = P_x (f16, written by softmax group x into SW128 smem),
-//                   B = V tile (MN-major: keys are the contraction dim)               -> TMEM O_x[j&1] (64 cols each)
-// Online softmax (running max / sum, f32) lives in registers of 128 threads per tile (one query row each). The
-// per-block P V result is double-buffered in TMEM and folded into the register accumulator one block late, so
-// the softmax warps never wait for the tensor pipe in steady state and TMEM never needs a read-modify-write.
+// Flash-style on tcgen05 tensor cores; scores, probabilities and the output accumulator all live in TMEM:
+//   S_x = Q_x K^T : A = Q tile (K-major, TMA SW128 smem), B = K tile (K-major smem)        -> TMEM S_x (128 f32 columns)
+//   P_x           : written by the softmax warps straight back to TMEM as packed f16 (tcgen05.st, 64 columns)
+//   O_x += P_x V  : A = P_x FROM TMEM, B = V tile (MN-major smem: keys are the contraction)  -> TMEM O_x (64 f32 columns)
+// One CTA works on TWO 128-query tiles (slots A, B) of one head and streams the 128-key blocks once for both; two softmax
+// warpgroups (one thread per query row) ping-pong against one MMA issuer, so the tensor pipe runs slot B's P V / Q K^T while
+// slot A is in its exp phase and vice versa. O accumulates in TMEM across key blocks (no per-block read-back): the exponent
+// reference of a row is lazy (re-based only when the running max grew by more than 2^8; exact max for the first block, warp-
+// uniform overflow-safe redo), and the rare re-base rescales the row's O in TMEM in place. The CTA is persistent over a
+// contiguous range of (batch, head, query tile) work items and all barriers run with continuous phases, so the Q load, first
+// Q K^T and the output write-back of consecutive items overlap (no drain / re-initialisation between items).
+// The exp work (MUFU ex2 + the f32->f16 pack, both on the XU pipe) is what bounds d = 64 attention, so a compile-time
+// fraction of the exponentials is evaluated on the FMA pipe instead (Cody-Waite range reduction + degree-4 polynomial,
+// max relative error 3e-6, far below the f16 rounding of P).
 // Warp roles (320 threads): warp0 TMA producer, warp1 MMA issuer + TMEM owner, warps 2..5 softmax A, 6..9 softmax B.
+// TMEM columns: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384) P_A [384,448) P_B [448,512).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -19,43 +25,165 @@
 namespace sdxl {
 
 static constexpr int kTileBytes = 128 * 128;        // 128 rows x 64 halves (Q, K or V tile)
-static constexpr int kPBytes = 2 * 128 * 128;       // 128 rows x 128 keys, two 64-key swizzle panels
-static constexpr int kXchgBytes = 2 * 2 * 2 * 128 * 4;  // SPLIT=2: [slot][group][column half][row] f32
-static constexpr int kAttnSmem = 2 * kTileBytes + 4 * kTileBytes + 2 * kPBytes + 256 + kXchgBytes;
-// SPLIT = threads per query row in the softmax groups: 1 -> warps 2..5 / 6..9 (320 threads),
-// 2 -> warps 2..9 / 10..17 (576 threads): each thread owns 64 of a block's 128 score columns and 32 of the 64 output columns,
-// twice as many warps per scheduler to cover the tcgen05.ld latency.
-template <int SPLIT> struct AttnCfg { static constexpr int kThreads = 64 + 256 * SPLIT; };
+static constexpr int kKvStages = 3;
+static constexpr int kQSlots = 4;                   // ring of two items x two slots
+static constexpr int kAttnSmem = kQSlots * kTileBytes + 2 * kKvStages * kTileBytes + 512;
+static constexpr int kAttnThreads = 320;
+static constexpr uint32_t kColS = 0, kColO = 256, kColP = 384;
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x on the FMA / ALU pipes: t = x + 1.5*2^23 rounded towards -inf keeps floor(x) in the low mantissa bits; r = x - floor(x)
+// in [0,1); 2^r by a degree-4 minimax polynomial (max rel. error 3.0e-6); the integer part goes straight into the exponent
+// field. x is clamped at -126 (results below 2^-126 are irrelevant: P is rounded to f16 afterwards).
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.0f);
+  float t;
+  asm("add.rm.ftz.f32 %0, %1, 0f4B400000;" : "=f"(t) : "f"(x));
+  const float r = x - (t - 12582912.0f);
+  float p = fmaf(0.013426684f, r, 0.052242474f);
+  p = fmaf(p, r, 0.241280205f);
+  p = fmaf(p, r, 0.693044845f);
+  p = fmaf(p, r, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 
-template <int SPLIT>
-__global__ void __launch_bounds__(AttnCfg<SPLIT>::kThreads, 1) attention_kernel(const __grid_constant__ AttnParams p) {
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+      "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+        "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+        "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// Four K=16 MMAs of S = Q K^T (both operands in SW128 smem, 32-byte descriptor steps) + commit, one elect.
+__device__ __forceinline__ void mma_qk_commit(uint32_t d_tmem, uint32_t q_lo, uint32_t k_lo, uint32_t desc_hi, uint32_t idesc,
+                                              uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e, t, f;\n\t"
+      ".reg .b64 da, db;\n\t"
+      ".reg .b32 al, bl;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.eq.b32 t, 0, 0;\n\t"
+      "setp.ne.b32 f, 0, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, f;\n\t"
+      "add.u32 al, %1, 2;\n\t"
+      "add.u32 bl, %2, 2;\n\t"
+      "mov.b64 da, {al, %3};\n\t"
+      "mov.b64 db, {bl, %3};\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, t;\n\t"
+      "add.u32 al, %1, 4;\n\t"
+      "add.u32 bl, %2, 4;\n\t"
+      "mov.b64 da, {al, %3};\n\t"
+      "mov.b64 db, {bl, %3};\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, t;\n\t"
+      "add.u32 al, %1, 6;\n\t"
+      "add.u32 bl, %2, 6;\n\t"
+      "mov.b64 da, {al, %3};\n\t"
+      "mov.b64 db, {bl, %3};\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, t;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t"
+      "}"
+      ::"r"(d_tmem), "r"(q_lo), "r"(k_lo), "r"(desc_hi), "r"(idesc), "r"(smem_u32(bar))
+      : "memory");
+}
+// Eight K=16 MMAs of O (+)= P V: A = P in TMEM (8 columns of packed f16 per step), B = V in smem (MN-major, 16 key rows =
+// 2048 B per step). `acc_first` = accumulate flag of the first MMA (0 for the first key block of a work item).
+__device__ __forceinline__ void mma_pv(uint32_t d_tmem, uint32_t p_tmem, uint32_t v_lo, uint32_t desc_hi, uint32_t idesc,
+                                       uint32_t acc_first) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e, t, p;\n\t"
+      ".reg .b64 db;\n\t"
+      ".reg .b32 pa, bl;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.eq.b32 t, 0, 0;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t"
+      "add.u32 pa, %1, 8;\n\t   add.u32 bl, %2, 128;\n\t  mov.b64 db, {bl, %3};\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [pa], db, %4, t;\n\t"
+      "add.u32 pa, %1, 16;\n\t  add.u32 bl, %2, 256;\n\t  mov.b64 db, {bl, %3};\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [pa], db, %4, t;\n\t"
+      "add.u32 pa, %1, 24;\n\t  add.u32 bl, %2, 384;\n\t  mov.b64 db, {bl, %3};\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [pa], db, %4, t;\n\t"
+      "add.u32 pa, %1, 32;\n\t  add.u32 bl, %2, 512;\n\t  mov.b64 db, {bl, %3};\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [pa], db, %4, t;\n\t"
+      "add.u32 pa, %1, 40;\n\t  add.u32 bl, %2, 640;\n\t  mov.b64 db, {bl, %3};\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [pa], db, %4, t;\n\t"
+      "add.u32 pa, %1, 48;\n\t  add.u32 bl, %2, 768;\n\t  mov.b64 db, {bl, %3};\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [pa], db, %4, t;\n\t"
+      "add.u32 pa, %1, 56;\n\t  add.u32 bl, %2, 896;\n\t  mov.b64 db, {bl, %3};\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [pa], db, %4, t;\n\t"
+      "}"
+      ::"r"(d_tmem), "r"(p_tmem), "r"(v_lo), "r"(desc_hi), "r"(idesc), "r"(acc_first)
+      : "memory");
+}
+
+// One 32-column chunk of a score row: p = 2^(s*c - mb) -> packed f16 (16 words); tracks the row's block max (two chains) and
+// the f32 sum. POLY = 0: every exponential on the MUFU; 1: every 4th on the FMA pipe; 2: every 2nd.
+template <int POLY>
+__device__ __forceinline__ void softmax_chunk(const uint32_t (&v)[32], uint32_t (&h)[16], float sl2e, float mb, float& b0, float& b1,
+                                              float& sum, bool ragged, int col0, int S) {
+  float s_a = 0.f, s_b = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
+    if (ragged) {
+      if (col0 + i >= S) s0 = -INFINITY;
+      if (col0 + i + 1 >= S) s1 = -INFINITY;
+    }
+    b0 = fmaxf(b0, s0);
+    b1 = fmaxf(b1, s1);
+    const float x0 = fmaf(s0, sl2e, -mb), x1 = fmaf(s1, sl2e, -mb);
+    const float p0 = ex2_approx(x0);
+    const bool poly1 = (POLY == 2) || (POLY == 1 && (i & 2));
+    const float p1 = poly1 ? ex2_poly(x1) : ex2_approx(x1);
+    s_a += p0;
+    s_b += p1;
+    __half2 t = __floats2half2_rn(p0, p1);
+    h[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
+  }
+  sum += s_a + s_b;
+}
+
+template <int POLY>
+__global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sQ = smem;                       // [2] tiles A, B
-  uint8_t* sK = sQ + 2 * kTileBytes;        // [2] stages
-  uint8_t* sV = sK + 2 * kTileBytes;        // [2] stages
-  uint8_t* sP = sV + 2 * kTileBytes;        // [2] groups
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kPBytes);
-  uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;    // [2]
-  uint64_t* kv_empty = bars + 3;   // [2]
-  uint64_t* s_full = bars + 5;     // [2] per group
-  uint64_t* p_full = bars + 7;     // [2] per group, 128 arrivals
-  uint64_t* pv_done = bars + 9;    // [2] per group
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 11);
-  float* xchg = reinterpret_cast<float*>(sP + 2 * kPBytes + 256);   // SPLIT=2 pair exchange slots
+  uint8_t* sQ = smem;                                  // [kQSlots]
+  uint8_t* sK = sQ + kQSlots * kTileBytes;             // [kKvStages]
+  uint8_t* sV = sK + kKvStages * kTileBytes;           // [kKvStages]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kKvStages * kTileBytes);
+  uint64_t* q_full = bars;                       // [4]
+  uint64_t* q_empty = q_full + kQSlots;          // [4]
+  uint64_t* kv_full = q_empty + kQSlots;         // [3]
+  uint64_t* kv_empty = kv_full + kKvStages;      // [3]
+  uint64_t* s_full = kv_empty + kKvStages;       // [2] per slot
+  uint64_t* p_full = s_full + 2;                 // [2] per slot, 128 arrivals
+  uint64_t* o_full = p_full + 2;                 // [2] per slot
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nblk = (p.S + 127) / 128;
-  // Persistent: the (batch, head, 128-query tile) work list is split into contiguous, balanced ranges, one per
-  // CTA; inside its range a CTA takes two consecutive tiles of the same head as a ping-pong pair, a single
-  // tile otherwise (end of a head or of the range). This removes most of the wave-quantisation loss of a
-  // one-pair-per-CTA grid (e.g. 320 tiles on 148 SMs: 1 pair + 1 single instead of 2 full waves).
+  // Persistent: the (batch, head, 128-query tile) work list is split into contiguous, balanced ranges, one per CTA; inside
+  // its range a CTA takes two consecutive tiles of the same head as a two-slot item, a single tile otherwise.
   const int nqt = (p.T + 127) / 128;
   const long total_tiles = (long)p.B * p.n_head * nqt;
   const int t_begin = (int)(total_tiles * blockIdx.x / gridDim.x);
@@ -69,6 +197,10 @@ __global__ void __launch_bounds__(AttnCfg<SPLIT>::kThreads, 1) attention_kernel(
     tma_prefetch_desc(&p.tmQ);
     tma_prefetch_desc(&p.tmK);
     tma_prefetch_desc(&p.tmV);
+    for (int i = 0; i < kQSlots; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
+    for (int i = 0; i < kKvStages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&o_full[i], 1); }
+    fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, 512);
   tc_fence_before();
@@ -78,38 +210,29 @@ __global__ void __launch_bounds__(AttnCfg<SPLIT>::kThreads, 1) attention_kernel(
   griddep_wait();  // PDL: the prologue above overlapped the previous kernel's tail
   griddep_launch_dependents();
 
-  for (int tile = t_begin; tile < t_end;) {
-  const int qt = tile % nqt;
-  const int head = (tile / nqt) % p.n_head;
-  const int b = tile / (nqt * p.n_head);
-  const int row0 = qt * 128;
-  const bool hasB = (qt + 1 < nqt) && (tile + 1 < t_end);   // pair with the next tile of the same head
-  tile += hasB ? 2 : 1;
-  // fresh barriers for every work item (nobody is using them here: see the __syncthreads at the loop end)
-  if (threadIdx.x == 0) {
-    mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
-      mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128 * SPLIT);
-      mbar_init(&pv_done[i], 1);
-    }
-    fence_barrier_init();
-  }
-  __syncthreads();
-
   if (warp == 0) {
+    // ===================== TMA producer =====================
     if (lane == 0) {
-      mbar_expect_tx(q_full, (hasB ? 2 : 1) * kTileBytes);
-      tma_load_3d(sQ, &p.tmQ, q_full, p.q_col0 + head * 64, row0, b);
-      if (hasB) tma_load_3d(sQ + kTileBytes, &p.tmQ, q_full, p.q_col0 + head * 64, row0 + 128, b);
-      for (int j = 0; j < nblk; ++j) {
-        const int stage = j & 1;
-        mbar_wait(&kv_empty[stage], ((j >> 1) & 1) ^ 1);
-        mbar_expect_tx(&kv_full[stage], 2 * kTileBytes);
-        tma_load_3d(sK + stage * kTileBytes, &p.tmK, &kv_full[stage], p.k_col0 + head * 64, j * 128, b);
-        tma_load_3d(sV + stage * kTileBytes, &p.tmV, &kv_full[stage], p.v_col0 + head * 64, j * 128, b);
+      uint32_t qe_ph = 0;
+      int kvc = 0, item = 0;
+      for (int tile = t_begin; tile < t_end; ++item) {
+        const int qt = tile % nqt, head = (tile / nqt) % p.n_head, b = tile / (nqt * p.n_head);
+        const bool hasB = (qt + 1 < nqt) && (tile + 1 < t_end);
+        tile += hasB ? 2 : 1;
+        for (int x = 0; x < (hasB ? 2 : 1); ++x) {
+          const int qs = (item & 1) * 2 + x;
+          mbar_wait(&q_empty[qs], ((qe_ph >> qs) & 1u) ^ 1u);
+          qe_ph ^= 1u << qs;
+          mbar_expect_tx(&q_full[qs], kTileBytes);
+          tma_load_3d(sQ + qs * kTileBytes, &p.tmQ, &q_full[qs], p.q_col0 + head * 64, qt * 128 + x * 128, b);
+        }
+        for (int j = 0; j < nblk; ++j, ++kvc) {
+          const int st = kvc % kKvStages;
+          mbar_wait(&kv_empty[st], ((kvc / kKvStages) & 1) ^ 1);
+          mbar_expect_tx(&kv_full[st], 2 * kTileBytes);
+          tma_load_3d(sK + st * kTileBytes, &p.tmK, &kv_full[st], p.k_col0 + head * 64, j * 128, b);
+          tma_load_3d(sV + st * kTileBytes, &p.tmV, &kv_full[st], p.v_col0 + head * 64, j * 128, b);
+        }
       }
     }
   } else if (warp == 1) {
@@ -121,365 +244,227 @@ __global__ void __launch_bounds__(AttnCfg<SPLIT>::kThreads, 1) attention_kernel(
     const uint32_t q_lo0 = ((smem_u32(sQ) >> 4) & 0x3FFFu) | lo_flag;
     const uint32_t k_lo0 = ((smem_u32(sK) >> 4) & 0x3FFFu) | lo_flag;
     const uint32_t v_lo0 = ((smem_u32(sV) >> 4) & 0x3FFFu) | lo_flag;
-    const uint32_t p_lo0 = ((smem_u32(sP) >> 4) & 0x3FFFu) | lo_flag;
-    constexpr uint32_t kTile16 = kTileBytes >> 4, kP16 = kPBytes >> 4;
-    // S_x = Q_x K_stage^T
-    auto issue_qk = [&](int x, int stage) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        tc_mma_f16_elect(tmem_base + x * 128, q_lo0 + x * kTile16 + 2 * k, k_lo0 + stage * kTile16 + 2 * k, dhi, idesc_qk, k > 0);
-      tc_commit_elect(&s_full[x]);
-    };
-    // O_x[j&1] = P_x V_j   (P panel t>>2 is 16 KB further, 32 B per 16 keys; V: 16 key rows = 2048 B)
-    auto issue_pv = [&](int x, int j) {
-      const uint32_t d = tmem_base + 256 + x * 128 + (j & 1) * 64;
-#pragma unroll
-      for (int t = 0; t < 8; ++t)
-        tc_mma_f16_elect(d, p_lo0 + x * kP16 + (t >> 2) * 1024 + (t & 3) * 2, v_lo0 + (j & 1) * kTile16 + t * 128, dhi, idesc_pv,
-                         t > 0);
-      tc_commit_elect(&pv_done[x]);
-    };
-    mbar_wait(q_full, 0);
-    mbar_wait(&kv_full[0], 0);
-    tc_fence_after();
-    issue_qk(0, 0);
-    if (hasB) issue_qk(1, 0);
-    for (int j = 0; j < nblk; ++j) {
-      const bool more = j + 1 < nblk;
-      mbar_wait(&p_full[0], j & 1);  // P_A(j) written, S_A(j) consumed
-      tc_fence_after();
-      issue_pv(0, j);
-      if (more) {
-        mbar_wait(&kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
-        tc_fence_after();
-        issue_qk(0, (j + 1) & 1);
-      }
+    constexpr uint32_t kTile16 = kTileBytes >> 4;
+    uint32_t qf_ph = 0, pf_ph = 0;
+    int kvc = 0, item = 0;
+    for (int tile = t_begin; tile < t_end; ++item) {
+      const int qt = tile % nqt;
+      const bool hasB = (qt + 1 < nqt) && (tile + 1 < t_end);
+      tile += hasB ? 2 : 1;
+      const int qs0 = (item & 1) * 2;
+      mbar_wait(&q_full[qs0], (qf_ph >> qs0) & 1u);
+      qf_ph ^= 1u << qs0;
       if (hasB) {
-        mbar_wait(&p_full[1], j & 1);
-        tc_fence_after();
-        issue_pv(1, j);
+        mbar_wait(&q_full[qs0 + 1], (qf_ph >> (qs0 + 1)) & 1u);
+        qf_ph ^= 1u << (qs0 + 1);
       }
-      tc_commit_elect(&kv_empty[j & 1]);  // K_j / V_j no longer needed once everything issued so far retires
-      if (more && hasB) issue_qk(1, (j + 1) & 1);
-    }
-    // drain: the last stage releases have no consumer; observe them so that no asynchronous arrival is still
-    // in flight when the barriers are re-initialised for the next work item
-    for (int s = 0; s < 2 && s < nblk; ++s) {
-      const int uses = (nblk - s + 1) >> 1;  // blocks j with (j & 1) == s
-      mbar_wait(&kv_empty[s], (uses - 1) & 1);
+      int st = kvc % kKvStages;
+      mbar_wait(&kv_full[st], (kvc / kKvStages) & 1);
+      tc_fence_after();
+      mma_qk_commit(tmem_base + kColS, q_lo0 + qs0 * kTile16, k_lo0 + st * kTile16, dhi, idesc_qk, &s_full[0]);
+      if (hasB) mma_qk_commit(tmem_base + kColS + 128, q_lo0 + (qs0 + 1) * kTile16, k_lo0 + st * kTile16, dhi, idesc_qk, &s_full[1]);
+      for (int j = 0; j < nblk; ++j, ++kvc) {
+        const bool more = j + 1 < nblk;
+        st = kvc % kKvStages;
+        const int stn = (kvc + 1) % kKvStages;
+        // ---- slot A: O_A (+)= P_A V_j, then S_A = Q_A K_{j+1}^T
+        mbar_wait(&p_full[0], pf_ph & 1u);
+        pf_ph ^= 1u;
+        tc_fence_after();
+        mma_pv(tmem_base + kColO, tmem_base + kColP, v_lo0 + st * kTile16, dhi, idesc_pv, j > 0 ? 1u : 0u);
+        if (more) {
+          mbar_wait(&kv_full[stn], ((kvc + 1) / kKvStages) & 1);
+          tc_fence_after();
+          mma_qk_commit(tmem_base + kColS, q_lo0 + qs0 * kTile16, k_lo0 + stn * kTile16, dhi, idesc_qk, &s_full[0]);
+        } else {
+          tc_commit_elect(&o_full[0]);
+          tc_commit_elect(&q_empty[qs0]);
+        }
+        // ---- slot B
+        if (hasB) {
+          mbar_wait(&p_full[1], (pf_ph >> 1) & 1u);
+          pf_ph ^= 2u;
+          tc_fence_after();
+          mma_pv(tmem_base + kColO + 64, tmem_base + kColP + 64, v_lo0 + st * kTile16, dhi, idesc_pv, j > 0 ? 1u : 0u);
+        }
+        tc_commit_elect(&kv_empty[st]);   // K_j / V_j are free once everything issued so far retires
+        if (hasB) {
+          if (more) {
+            mma_qk_commit(tmem_base + kColS + 128, q_lo0 + (qs0 + 1) * kTile16, k_lo0 + stn * kTile16, dhi, idesc_qk, &s_full[1]);
+          } else {
+            tc_commit_elect(&o_full[1]);
+            tc_commit_elect(&q_empty[qs0 + 1]);
+          }
+        }
+      }
     }
   } else {
-    if constexpr (SPLIT == 1) {
-    const int x = (warp - 2) >> 2;  // softmax group: 0 = tile A, 1 = tile B
-    if (x == 0 || hasB) {
-      const int q = warp & 3;
-      const int r = q * 32 + lane;  // query row in tile == TMEM lane
-      const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-      const uint32_t tS = tmem_base + lane_off + x * 128;
-      const uint32_t tO = tmem_base + lane_off + 256 + x * 128;
-      const float sl2e = p.scale_log2e;
-      float m = -INFINITY, m_prev = -INFINITY, l = 0.f, alpha_prev = 0.f;
-      float O[64];
-#pragma unroll
-      for (int i = 0; i < 64; ++i) O[i] = 0.f;
-      uint8_t* prow = sP + x * kPBytes + (r >> 3) * 1024 + (r & 7) * 128;
-      const int rx = r & 7;
-
+    // ===================== softmax warpgroups: one thread per query row =====================
+    const int x = (warp - 2) >> 2;   // slot: 0 = tile A, 1 = tile B
+    const int q = warp & 3;          // TMEM lane quarter this warp may access (hardware: warp id % 4)
+    const int r = q * 32 + lane;     // query row in the tile == TMEM lane
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t tS = tmem_base + lane_off + kColS + x * 128;
+    const uint32_t tO = tmem_base + lane_off + kColO + x * 64;
+    const uint32_t tP = tmem_base + lane_off + kColP + x * 64;
+    const float sl2e = p.scale_log2e;
+    uint32_t s_ph = 0, o_ph = 0;
+    for (int tile = t_begin; tile < t_end;) {
+      const int qt = tile % nqt, head = (tile / nqt) % p.n_head, b = tile / (nqt * p.n_head);
+      const bool hasB = (qt + 1 < nqt) && (tile + 1 < t_end);
+      tile += hasB ? 2 : 1;
+      if (x == 1 && !hasB) continue;
+      float m = -INFINITY, m_prev = -INFINITY, l = 0.f;
       for (int j = 0; j < nblk; ++j) {
-        mbar_wait(&s_full[x], j & 1);
-        // P V of block j-1 was issued before Q K^T of block j, so it has retired too. Observe its phase NOW,
-        // before this thread's p_full arrival lets the MMA warp issue P V of block j (a waiter must never
-        // fall two phases behind an mbarrier).
-        if (j > 0) mbar_wait(&pv_done[x], (j - 1) & 1);
+        mbar_wait(&s_full[x], s_ph);   // S(j) complete; it was issued after P V of block j-1, so O(j-1) is complete too
+        s_ph ^= 1u;
         tc_fence_after();
         const int kbase = j * 128;
         const bool ragged = kbase + 128 > p.S;
-        // Reference for the exponent. Block 0: exact row max (one extra pass over S). Later blocks: the reference
-        // decided at the end of the previous block (lazy max): p = exp2((s - ref) * c) may exceed 1 (f16 P and f32
-        // sums have the head-room), and the row's running max is folded in only when it grew by more than 2^8.
-        // An overflow-safe redo (warp-uniform, practically never taken) re-runs the block with the exact max.
+        // Exponent reference. Block 0: exact row max (one extra pass over S). Later blocks: the reference decided at the end
+        // of the previous block (lazy): p = 2^((s - ref) c) may exceed 1 (f16 P and the f32 sums have the head-room).
         float ref = m;
         if (j == 0) {
-          float mx = -INFINITY;
+          float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll 1
           for (int c = 0; c < 128; c += 32) {
+            if (kbase + c >= p.S) break;
             uint32_t v[32];
             tmem_ld32(tS + c, v);
             tmem_ld_wait();
-            if (!ragged) {
-              float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;  // four short chains
 #pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                m0 = fmaxf(m0, __uint_as_float(v[i]));
-                m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
-                m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
-                m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
-              }
-              mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (kbase + c + i < p.S) mx = fmaxf(mx, __uint_as_float(v[i]));
+            for (int i = 0; i < 32; i += 4) {
+              if (!ragged || kbase + c + i < p.S) m0 = fmaxf(m0, __uint_as_float(v[i]));
+              if (!ragged || kbase + c + i + 1 < p.S) m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
+              if (!ragged || kbase + c + i + 2 < p.S) m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
+              if (!ragged || kbase + c + i + 3 < p.S) m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
             }
           }
-          ref = mx;
+          ref = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
         }
-        float alpha, sum, bmax;
+        float sum, bmax;
         bool redo;
         do {
-          alpha = ex2_approx((m_prev - ref) * sl2e);   // rescale of everything accumulated so far (0 for block 0)
           const float mb = ref * sl2e;
           sum = 0.f;
           float b0 = -INFINITY, b1 = -INFINITY;
-          // p = exp2(s*scale - ref*scale) -> f16 -> swizzled smem (A operand of the PV MMA); track the block max
-#pragma unroll 1
-          for (int c = 0; c < 128; c += 32) {
-            uint32_t v[32];
-            tmem_ld32(tS + c, v);
+          // software pipeline over the four 32-column chunks: the TMEM load of chunk c+1 flies while chunk c is exponentiated
+          uint32_t va[32], vb[32], h[16];
+          tmem_ld32(tS, va);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
             tmem_ld_wait();
-            uint32_t h[16];
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
-              if (ragged) {
-                if (kbase + c + i >= p.S) s0 = -INFINITY;
-                if (kbase + c + i + 1 >= p.S) s1 = -INFINITY;
-              }
-              b0 = fmaxf(b0, s0);
-              b1 = fmaxf(b1, s1);
-              const float p0 = ex2_approx(fmaf(s0, sl2e, -mb));
-              const float p1 = ex2_approx(fmaf(s1, sl2e, -mb));
-              sum += p0 + p1;
-              __half2 t = __floats2half2_rn(p0, p1);
-              h[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
+            const bool live = kbase + c * 32 < p.S;          // warp-uniform: chunk has at least one valid key
+            const bool next_live = c < 3 && kbase + (c + 1) * 32 < p.S;
+            if (c & 1) {
+              if (next_live) tmem_ld32(tS + (c + 1) * 32, va);
+              if (live) softmax_chunk<POLY>(vb, h, sl2e, mb, b0, b1, sum, ragged, kbase + c * 32, p.S);
+            } else {
+              if (next_live) tmem_ld32(tS + (c + 1) * 32, vb);
+              if (live) softmax_chunk<POLY>(va, h, sl2e, mb, b0, b1, sum, ragged, kbase + c * 32, p.S);
             }
-            uint8_t* panel = prow + (c >> 6) * (128 * 128);
-            const int ch0 = (c & 63) >> 3;  // first 16B chunk of this 32-key group inside the 128B row
+            if (!live) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-              *reinterpret_cast<uint4*>(panel + (((ch0 + u) ^ rx) << 4)) =
-                  make_uint4(h[4 * u], h[4 * u + 1], h[4 * u + 2], h[4 * u + 3]);
+              for (int i = 0; i < 16; ++i) h[i] = 0u;
+            }
+            tmem_st16(tP + c * 16, h);
           }
           bmax = fmaxf(b0, b1);
-          // f16 P overflows beyond 2^16: redo the whole block (all lanes: the TMEM loads are warp-collective)
+          // f16 P overflows beyond 2^16: redo the whole block with the exact max (all lanes: the TMEM ops are warp-collective)
           const bool over = (bmax - ref) * sl2e > 15.0f;
           redo = __any_sync(0xffffffffu, over);
           if (over) ref = bmax;
+          if (redo) tmem_st_wait();
         } while (redo);
-        l = l * alpha + sum;
+        if (j > 0) {
+          // the row's reference moved: rescale what has been accumulated so far (rare; O(j-1) is complete, see above)
+          const bool moved = ref != m_prev;
+          if (__any_sync(0xffffffffu, moved)) {
+            const float alpha = moved ? ex2_approx((m_prev - ref) * sl2e) : 1.0f;
+            l *= alpha;
+#pragma unroll 1
+            for (int c = 0; c < 64; c += 32) {
+              uint32_t o[32];
+              tmem_ld32(tO + c, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st32(tO + c, o);
+            }
+          }
+        }
+        l += sum;
         m_prev = ref;
         m = ((bmax - ref) * sl2e > 8.0f) ? bmax : ref;   // reference for the next block
-        fence_proxy_async_smem();
+        tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&p_full[x]);
-        // fold in the PREVIOUS block's P V (already complete: it was issued before this block's Q K^T)
-        if (j > 0) {
-          const uint32_t to = tO + ((j - 1) & 1) * 64;
-#pragma unroll
-          for (int c = 0; c < 64; c += 32) {
-            uint32_t v[32];
-            tmem_ld32(to + c, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) O[c + i] = fmaf(O[c + i], alpha_prev, __uint_as_float(v[i]));
-          }
-        }
-        alpha_prev = alpha;
       }
-      {
-        const int j = nblk - 1;
-        mbar_wait(&pv_done[x], j & 1);
-        tc_fence_after();
-        const uint32_t to = tO + (j & 1) * 64;
-#pragma unroll
-        for (int c = 0; c < 64; c += 32) {
-          uint32_t v[32];
-          tmem_ld32(to + c, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) O[c + i] = fmaf(O[c + i], alpha_prev, __uint_as_float(v[i]));
-        }
-      }
-      const int t = row0 + x * 128 + r;
-      if (t < p.T) {
-        const float inv = 1.0f / l;
-        __half* o = p.out + ((size_t)b * p.T + t) * p.ldo + head * 64;
-#pragma unroll
-        for (int c = 0; c < 64; c += 8) {
-          uint32_t h[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            __half2 t2 = __floats2half2_rn(O[c + 2 * i] * inv, O[c + 2 * i + 1] * inv);
-            h[i] = *reinterpret_cast<uint32_t*>(&t2);
-          }
-          *reinterpret_cast<uint4*>(o + c) = make_uint4(h[0], h[1], h[2], h[3]);
-        }
-      }
-    }
-    } else {
-    // ---------- SPLIT == 2: two threads per query row ----------
-    const int sw = warp - 2;              // 0..15
-    const int x = sw >> 3;                // softmax group: 0 = tile A, 1 = tile B
-    if (x == 0 || hasB) {
-      const int q = warp & 3;             // TMEM lane quarter this warp may access (hardware: warp id % 4)
-      const int ch = (sw >> 2) & 1;       // column half: score columns [64 ch, 64 ch + 64), output columns [32 ch, 32 ch + 32)
-      const int r = q * 32 + lane;        // query row in tile == TMEM lane
-      const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-      const uint32_t tS = tmem_base + lane_off + x * 128 + ch * 64;
-      const uint32_t tO = tmem_base + lane_off + 256 + x * 128 + ch * 32;
-      const float sl2e = p.scale_log2e;
-      const int bar_id = 1 + x * 4 + q;   // named barrier of the two warps that share these 32 rows
-      int xk = 0;                         // exchange counter (slot = xk & 1)
-      // combine a per-thread value with the partner thread of the same row (other column half)
-      auto exchange = [&](float v) {
-        float* slot = xchg + (((xk & 1) * 2 + x) * 2) * 128;
-        slot[ch * 128 + r] = v;
-        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-        const float o = slot[(ch ^ 1) * 128 + r];
-        ++xk;
-        return o;
-      };
-      float m = -INFINITY, m_prev = -INFINITY, l = 0.f, alpha_prev = 0.f;
-      float O[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) O[i] = 0.f;
-      uint8_t* prow = sP + x * kPBytes + ch * (128 * 128) + (r >> 3) * 1024 + (r & 7) * 128;   // my 64-key panel
-      const int rx = r & 7;
-
-      for (int j = 0; j < nblk; ++j) {
-        mbar_wait(&s_full[x], j & 1);
-        if (j > 0) mbar_wait(&pv_done[x], (j - 1) & 1);
-        tc_fence_after();
-        const int kbase = j * 128 + ch * 64;
-        const bool ragged = j * 128 + 128 > p.S;
-        float ref = m;
-        if (j == 0) {
-          float mx = -INFINITY;
+      // ---- write-back: O / l -> f16 (the next item's Q K^T and first exp phase overlap this)
+      mbar_wait(&o_full[x], o_ph);
+      o_ph ^= 1u;
+      tc_fence_after();
+      const int t = qt * 128 + x * 128 + r;
+      const float inv = 1.0f / l;
+      __half* o = p.out + ((size_t)b * p.T + t) * p.ldo + head * 64;
 #pragma unroll 1
-          for (int c = 0; c < 64; c += 32) {
-            uint32_t v[32];
-            tmem_ld32(tS + c, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (!ragged || kbase + c + i < p.S) mx = fmaxf(mx, __uint_as_float(v[i]));
-          }
-          ref = fmaxf(mx, exchange(mx));
-        }
-        float alpha, sum, bmax;
-        bool redo;
-        do {
-          alpha = ex2_approx((m_prev - ref) * sl2e);
-          const float mb = ref * sl2e;
-          sum = 0.f;
-          float b0 = -INFINITY, b1 = -INFINITY;
-#pragma unroll 1
-          for (int c = 0; c < 64; c += 32) {
-            uint32_t v[32];
-            tmem_ld32(tS + c, v);
-            tmem_ld_wait();
-            uint32_t h[16];
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
-              if (ragged) {
-                if (kbase + c + i >= p.S) s0 = -INFINITY;
-                if (kbase + c + i + 1 >= p.S) s1 = -INFINITY;
-              }
-              b0 = fmaxf(b0, s0);
-              b1 = fmaxf(b1, s1);
-              const float p0 = ex2_approx(fmaf(s0, sl2e, -mb));
-              const float p1 = ex2_approx(fmaf(s1, sl2e, -mb));
-              sum += p0 + p1;
-              __half2 t = __floats2half2_rn(p0, p1);
-              h[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
-            }
-            const int ch0 = c >> 3;  // first 16B chunk of this 32-key group inside my panel's 128B row
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              *reinterpret_cast<uint4*>(prow + (((ch0 + u) ^ rx) << 4)) = make_uint4(h[4 * u], h[4 * u + 1], h[4 * u + 2], h[4 * u + 3]);
-          }
-          const float bh = fmaxf(b0, b1);
-          bmax = fmaxf(bh, exchange(bh));   // block max of the whole row: both threads take identical decisions
-          const bool over = (bmax - ref) * sl2e > 15.0f;
-          redo = __any_sync(0xffffffffu, over);   // same rows in both warps of the pair -> same vote
-          if (over) ref = bmax;
-        } while (redo);
-        l = l * alpha + sum;   // partial sum over my columns; the halves are added once at the end
-        m_prev = ref;
-        m = ((bmax - ref) * sl2e > 8.0f) ? bmax : ref;
-        fence_proxy_async_smem();
-        tc_fence_before();
-        mbar_arrive(&p_full[x]);
-        if (j > 0) {
-          uint32_t v[32];
-          tmem_ld32(tO + ((j - 1) & 1) * 64, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) O[i] = fmaf(O[i], alpha_prev, __uint_as_float(v[i]));
-        }
-        alpha_prev = alpha;
-      }
-      {
-        const int j = nblk - 1;
-        mbar_wait(&pv_done[x], j & 1);
-        tc_fence_after();
+      for (int c = 0; c < 64; c += 32) {
         uint32_t v[32];
-        tmem_ld32(tO + (j & 1) * 64, v);
+        tmem_ld32(tO + c, v);
         tmem_ld_wait();
+        if (t < p.T) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) O[i] = fmaf(O[i], alpha_prev, __uint_as_float(v[i]));
-      }
-      const float lt = l + exchange(l);
-      const int t = row0 + x * 128 + r;
-      if (t < p.T) {
-        const float inv = 1.0f / lt;
-        __half* o = p.out + ((size_t)b * p.T + t) * p.ldo + head * 64 + ch * 32;
+          for (int u = 0; u < 4; ++u) {
+            uint32_t hh[4];
 #pragma unroll
-        for (int c = 0; c < 32; c += 8) {
-          uint32_t h[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            __half2 t2 = __floats2half2_rn(O[c + 2 * i] * inv, O[c + 2 * i + 1] * inv);
-            h[i] = *reinterpret_cast<uint32_t*>(&t2);
+            for (int i = 0; i < 4; ++i) {
+              __half2 t2 = __floats2half2_rn(__uint_as_float(v[8 * u + 2 * i]) * inv, __uint_as_float(v[8 * u + 2 * i + 1]) * inv);
+              hh[i] = *reinterpret_cast<uint32_t*>(&t2);
+            }
+            *reinterpret_cast<uint4*>(o + c + 8 * u) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
           }
-          *reinterpret_cast<uint4*>(o + c) = make_uint4(h[0], h[1], h[2], h[3]);
         }
       }
-    }
+      tc_fence_before();   // the TMEM reads above are ordered before this thread's next p_full arrival
     }
   }
 
   tc_fence_before();
-  __syncthreads();   // every role is done with this item's barriers, smem and TMEM
+  __syncthreads();   // every role is done: all MMAs retired (o_full observed), all barriers quiescent
   tc_fence_after();
-  }  // work items
-
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// Per-device launch state (several devices may be driven from one process: the opt-in to > 48 KB of dynamic shared memory
+// is a per-device function attribute).
+struct AttnDev { bool attr = false; int num_sms = 0; };
+static AttnDev g_attn_dev[64];
+static int g_attn_poly = -1;   // -1: default; sdxl_dbg_attention_variant sets 0 / 1 / 2
+void attention_set_variant(int poly) { g_attn_poly = poly; }
+
 int attention_launch(cudaStream_t st, const AttnParams& p) {
-  // SDXL_B200_ATTN_SPLIT=2 selects the two-threads-per-row softmax (16 softmax warps); default 1
-  static const int split = (getenv("SDXL_B200_ATTN_SPLIT") && atoi(getenv("SDXL_B200_ATTN_SPLIT")) == 2) ? 2 : 1;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  if (dev < 0 || dev >= 64) return 2001;
+  AttnDev& D = g_attn_dev[dev];
+  if (!D.attr) {
+    e = cudaFuncSetAttribute(attention_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
     if (e != cudaSuccess) return (int)e;
-    attr = true;
+    cudaDeviceGetAttribute(&D.num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (D.num_sms <= 0) D.num_sms = 148;
+    D.attr = true;
   }
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms <= 0) num_sms = 148;
-  }
+  static const int env_poly = getenv("SDXL_B200_ATTN_POLY") ? atoi(getenv("SDXL_B200_ATTN_POLY")) : 1;
+  const int poly = g_attn_poly >= 0 ? g_attn_poly : env_poly;
   const long tiles = (long)p.B * p.n_head * ((p.T + 127) / 128);
-  const long want = (tiles + 1) / 2;  // one pair per CTA when the machine is not full
-  dim3 grid((unsigned)(want < num_sms ? (want > 0 ? want : 1) : num_sms));
-  if (split == 2) return launch_kernel(attention_kernel<2>, grid, dim3(AttnCfg<2>::kThreads), (size_t)kAttnSmem, st, true, p);
-  return launch_kernel(attention_kernel<1>, grid, dim3(AttnCfg<1>::kThreads), (size_t)kAttnSmem, st, true, p);
+  const long want = (tiles + 1) / 2;  // one two-slot item per CTA when the machine is not full
+  dim3 grid((unsigned)(want < D.num_sms ? (want > 0 ? want : 1) : D.num_sms));
+  if (poly == 0) return launch_kernel(attention_kernel<0>, grid, dim3(kAttnThreads), (size_t)kAttnSmem, st, true, p);
+  if (poly == 2) return launch_kernel(attention_kernel<2>, grid, dim3(kAttnThreads), (size_t)kAttnSmem, st, true, p);
+  return launch_kernel(attention_kernel<1>, grid, dim3(kAttnThreads), (size_t)kAttnSmem, st, true, p);
 }
 
 }  // namespace sdxl

@@ -120,6 +120,7 @@ struct sdxl_unet {
   std::unique_ptr<Sampler> sampler;
   int* t_dev = nullptr;
   int* t_pinned = nullptr;
+  int t_slot = 0;              // ring position in t_pinned (per model: independent contexts never share it)
 };
 
 
@@ -685,8 +686,7 @@ static int run_plan(sdxl_unet* u) { return run_plan_ops(u->ctx, u->plan.get()); 
 
 static int set_t(sdxl_unet* u, int t) {
   sdxl_ctx* c = u->ctx;
-  static int slot = 0;
-  slot = (slot + 1) % 4096;
+  const int slot = u->t_slot = (u->t_slot + 1) % 4096;
   u->t_pinned[slot] = t;
   CU(c, cudaMemcpyAsync(u->t_dev, &u->t_pinned[slot], sizeof(int), cudaMemcpyHostToDevice, c->stream));
   return 0;
@@ -824,7 +824,7 @@ extern "C" int sdxl_unet_plan_num_ops(const sdxl_unet* u) { return (u && u->plan
 // sampler (Diffuser)
 // ================================================================================================
 struct Sampler {
-  int Bimg = 0, nfwd = 1, h = 0, w = 0;
+  int Bimg = 0, nfwd = 1, h = 0, w = 0, n_ctx = 0;
   float guidance = 1.f;
   float* noise = nullptr;  // scratch [Bimg,4,h,w]
   float* ref = nullptr;
@@ -857,11 +857,12 @@ static int sampler_begin(sdxl_unet* u, const sdxl_conditioning* cond, double gui
   if (Bimg < 1 || h < 1 || w < 1) return fail(c, 5202, "bad conditioning batch/resolution");
   Sampler* S = u->sampler.get();
   const size_t lat = (size_t)Bimg * g.in_channels * h * w;
-  if (!S || S->Bimg != Bimg || S->h != h || S->w != w || S->nfwd != nfwd) {
+  if (n_ctx < 1) return fail(c, 5202, "bad conditioning context length");
+  if (!S || S->Bimg != Bimg || S->h != h || S->w != w || S->nfwd != nfwd || S->n_ctx != n_ctx) {   // staging buffers are sized by all five
     CU(c, cudaStreamSynchronize(c->stream));
     u->sampler.reset(new Sampler());
     S = u->sampler.get();
-    S->Bimg = Bimg; S->nfwd = nfwd; S->h = h; S->w = w; S->latent_elems = lat;
+    S->Bimg = Bimg; S->nfwd = nfwd; S->h = h; S->w = w; S->n_ctx = n_ctx; S->latent_elems = lat;
     const size_t ctx_elems = (size_t)nfwd * Bimg * n_ctx * g.context_dim;
     const size_t y_elems = (size_t)nfwd * Bimg * g.adm_in_channels;
     if (S->arena.init(lat * 4 * 2 + lat + ctx_elems * 2 + y_elems * 2 + (1 << 16))) return fail(c, 5203, "cannot allocate sampler buffers");
@@ -911,11 +912,13 @@ extern "C" int sdxl_sampler_begin(sdxl_unet* u, const sdxl_conditioning* cond, d
 }
 extern "C" int sdxl_sampler_step(sdxl_unet* u, int t, int t_prev) {
   if (!u) return -1;
+  CU(u->ctx, cudaSetDevice(u->ctx->device));
   return sampler_step(u, t, t_prev);
 }
 extern "C" int sdxl_sampler_set_latent(sdxl_unet* u, const float* latent, int on_host) {
   if (!u || !u->sampler || !u->plan) return -1;
   sdxl_ctx* c = u->ctx;
+  CU(c, cudaSetDevice(c->device));
   CU(c, cudaMemcpyAsync(u->plan->x_in, latent, u->sampler->latent_elems * 4, on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, c->stream));
   if (on_host) CU(c, cudaStreamSynchronize(c->stream));
   return 0;
@@ -923,6 +926,7 @@ extern "C" int sdxl_sampler_set_latent(sdxl_unet* u, const float* latent, int on
 extern "C" int sdxl_sampler_get_latent(sdxl_unet* u, float* latent, int on_host) {
   if (!u || !u->sampler || !u->plan) return -1;
   sdxl_ctx* c = u->ctx;
+  CU(c, cudaSetDevice(c->device));
   CU(c, cudaMemcpyAsync(latent, u->plan->x_in, u->sampler->latent_elems * 4, on_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, c->stream));
   if (on_host) CU(c, cudaStreamSynchronize(c->stream));
   return 0;
@@ -930,6 +934,7 @@ extern "C" int sdxl_sampler_get_latent(sdxl_unet* u, float* latent, int on_host)
 extern "C" int sdxl_sampler_step_host(sdxl_unet* u, int t, int t_prev, float* latent_host) {
   if (!u || !u->sampler || !u->plan || !latent_host) return -1;
   sdxl_ctx* c = u->ctx;
+  CU(c, cudaSetDevice(c->device));
   Sampler* S = u->sampler.get();
   const size_t bytes = S->latent_elems * 4;
   memcpy(S->host_stage, latent_host, bytes);  // caller memory may be pageable: stage through pinned
@@ -943,6 +948,7 @@ extern "C" int sdxl_sampler_step_host(sdxl_unet* u, int t, int t_prev, float* la
 }
 extern "C" int sdxl_randn(sdxl_ctx* c, float* out, size_t n, uint64_t seed, uint64_t subsequence) {
   if (!c || !out) return -1;
+  CU(c, cudaSetDevice(c->device));
   KL(c, randn_launch(c->stream, out, n, seed, subsequence));
   return 0;
 }
@@ -1148,6 +1154,10 @@ extern "C" int sdxl_op_timestep_embedding(sdxl_ctx* c, const int32_t* t_host, in
   CU(c, cudaStreamSynchronize(c->stream));  // t_host is pageable caller memory
   return 0;
 }
+
+// Diagnostics: selects the attention kernel variant (fraction of exponentials on the FMA pipe: 0 none, 1 a quarter, 2 half;
+// -1 restores the default). Process-wide; used by tools/attn_bench.py and the parity tests to cover every variant.
+extern "C" void sdxl_dbg_attention_variant(int poly) { attention_set_variant(poly); }
 
 // Diagnostics: in-kernel timeline (%globaltimer, ns) of CTA 0 of one igemm launch on a synthetic [M,K]x[K,N] problem.
 // stamps_host[0..6] = prologue done, dependencies resolved, first operands landed, first accumulator complete,

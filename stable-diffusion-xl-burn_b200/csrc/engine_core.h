@@ -271,8 +271,21 @@ static int parse_pack(sdxl_ctx* c, const void* pack, size_t bytes, int on_device
   else memcpy(host_table.data(), (const uint8_t*)pack + sizeof h, tbytes);
   const PackEntry* e = (const PackEntry*)host_table.data();
   for (uint32_t i = 0; i < h.n_tensors; ++i) {
-    if (e[i].offset + e[i].nbytes > bytes) return fail(c, 4103, "weight pack: tensor '%.*s' out of range", 119, e[i].name);
+    if (e[i].nbytes > bytes || e[i].offset > bytes - e[i].nbytes) return fail(c, 4103, "weight pack: tensor '%.*s' out of range", 119, e[i].name);
     if (e[i].offset % 16) return fail(c, 4104, "weight pack: tensor '%.*s' not 16B aligned", 119, e[i].name);
+    if (e[i].ndim > 4 || e[i].dtype > 1) return fail(c, 4105, "weight pack: tensor '%.*s' has bad rank / dtype", 119, e[i].name);
+    {
+      uint64_t n = 1;   // element count, overflow-checked against the byte count the entry declares
+      bool ok = true;
+      for (uint32_t d = 0; d < e[i].ndim && ok; ++d) {
+        if (e[i].shape[d] != 0 && n > UINT64_MAX / e[i].shape[d]) ok = false;
+        else n *= e[i].shape[d];
+      }
+      const uint64_t esz = e[i].dtype ? 4 : 2;
+      if (!ok || n > UINT64_MAX / esz || n * esz != e[i].nbytes)
+        return fail(c, 4106, "weight pack: tensor '%.*s' declares %llu bytes but its shape needs a different size", 119, e[i].name,
+                    (unsigned long long)e[i].nbytes);
+    }
     std::string name(e[i].name, strnlen(e[i].name, sizeof e[i].name));
     pv.t[name] = e[i];
   }
@@ -283,7 +296,9 @@ static int parse_pack(sdxl_ctx* c, const void* pack, size_t bytes, int on_device
 // launch plan
 // ================================================================================================
 enum OpKind { OP_IGEMM, OP_ATTN, OP_GN, OP_LN, OP_GEMV, OP_TEMB, OP_CONV_IN, OP_UPS, OP_PHASE, OP_CAST16,
-              OP_SOFTMAX, OP_TRANSPOSE, OP_PQ, OP_EMBED, OP_ATTN_SMALL, OP_ACT, OP_LN_GATHER };
+              OP_SOFTMAX, OP_TRANSPOSE, OP_PQ, OP_EMBED, OP_ATTN_SMALL, OP_ACT, OP_LN_GATHER, OP_KIND_COUNT };
+// the public profile entry points take caller arrays of SDXL_PROFILE_KINDS entries (include/sdxl_b200.h)
+static_assert(OP_KIND_COUNT <= SDXL_PROFILE_KINDS, "profile arrays too small for the op kinds");
 static const char* const kOpNames[] = {"igemm", "attention", "group_norm", "layer_norm", "gemv", "temb", "conv_in", "upsample",
                                        "phase_split", "cast16", "softmax_rows", "transpose16", "post_quant", "embed_tokens",
                                        "attention_small", "mlp_act", "ln_gather"};
@@ -540,12 +555,13 @@ static int profile_plan_impl(sdxl_ctx* c, Plan* P, double* ms_by_kind, double* f
     if (!r && cudaEventRecord(ev[i + 1], c->stream) != cudaSuccess) r = -2;
   }
   cudaError_t se = cudaStreamSynchronize(c->stream);
-  for (int k = 0; k < 16; ++k) { ms_by_kind[k] = 0; flops_by_kind[k] = 0; launches_by_kind[k] = 0; }
+  for (int k = 0; k < SDXL_PROFILE_KINDS; ++k) { ms_by_kind[k] = 0; flops_by_kind[k] = 0; launches_by_kind[k] = 0; }
   if (!r && se == cudaSuccess)
     for (size_t i = 0; i < n; ++i) {
       float ms = 0;
       cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
       const int k = (int)P->ops[i].kind;
+      if (k < 0 || k >= SDXL_PROFILE_KINDS) continue;
       ms_by_kind[k] += ms;
       flops_by_kind[k] += P->ops[i].flops;
       launches_by_kind[k] += (P->ops[i].kind == OP_GN) ? 2 : 1;

@@ -144,6 +144,8 @@ struct AttnParams {
 };
 int make_tmap_rows(CUtensorMap* tm, const __half* base, int rows_per_batch, int nbatch, int cols, int pitch);
 int attention_launch(cudaStream_t st, const AttnParams& p);
+// diagnostics: fraction of the exponentials evaluated on the FMA pipe (0: none, 1: 1/4, 2: 1/2; -1: default / SDXL_B200_ATTN_POLY)
+void attention_set_variant(int poly);
 
 // ------------------------------------------------------------------------------------------------
 // Norms (norm.cu)

@@ -283,14 +283,14 @@ class Diffuser:
             self.set_conditioning(context, label)
         t = int(timesteps[0]) if hasattr(timesteps, "__len__") else int(timesteps)
         B, _, h, w = x.shape
+        # convert first, then enter: the ctx stream must wait for the cast / copy kernels torch queues on its own stream
+        f16 = x.dtype == torch.float16
+        x = x.to(ctx.device, torch.float16 if f16 else torch.float32).contiguous()
+        out = torch.empty_like(x)
         ctx.enter()
-        if x.dtype == torch.float16:
-            x = x.to(ctx.device).contiguous()
-            out = torch.empty_like(x)
+        if f16:
             rc = ctx.lib.sdxl_unet_forward(self.h, B, h, w, _ptr(x), t, _ptr(out))
         else:
-            x = x.to(ctx.device, torch.float32).contiguous()
-            out = torch.empty_like(x)
             rc = ctx.lib.sdxl_unet_forward_f32(self.h, B, h, w, _ptr(x), t, _ptr(out))
         ctx.check(rc, "sdxl_unet_forward")
         ctx.leave()
@@ -309,7 +309,7 @@ class Diffuser:
 
     def profile_plan(self) -> Dict[str, Dict[str, float]]:
         """Per-kernel-kind device time (ms), algorithmic FLOPs and launch count of one plan execution."""
-        ms, fl, ln = (C.c_double * 16)(), (C.c_double * 16)(), (C.c_int * 16)()
+        ms, fl, ln = (C.c_double * _lib.PROFILE_KINDS)(), (C.c_double * _lib.PROFILE_KINDS)(), (C.c_int * _lib.PROFILE_KINDS)()
         self.ctx.check(self.ctx.lib.sdxl_unet_profile_plan(self.h, ms, fl, ln), "sdxl_unet_profile_plan")
         return {n: {"ms": ms[i], "flops": fl[i], "launches": ln[i]} for i, n in enumerate(self.KIND_NAMES) if ln[i]}
 
@@ -489,7 +489,7 @@ class LatentDecoder:
         return float(self.ctx.lib.sdxl_vae_plan_flops(self.h))
 
     def profile_plan(self) -> Dict[str, Dict[str, float]]:
-        ms, fl, ln = (C.c_double * 16)(), (C.c_double * 16)(), (C.c_int * 16)()
+        ms, fl, ln = (C.c_double * _lib.PROFILE_KINDS)(), (C.c_double * _lib.PROFILE_KINDS)(), (C.c_int * _lib.PROFILE_KINDS)()
         self.ctx.check(self.ctx.lib.sdxl_vae_profile_plan(self.h, ms, fl, ln), "sdxl_vae_profile_plan")
         return {n: {"ms": ms[i], "flops": fl[i], "launches": ln[i]} for i, n in enumerate(self.KIND_NAMES) if ln[i]}
 

@@ -91,6 +91,22 @@ def test_group_norm(ctx, B, HW, C1, C2, silu):
     assert rel_err(out, ref) < 5e-4  # f16 output rounding (2^-11 relative per element)
 
 
+@pytest.mark.parametrize("B,HW,C,mean,std", [(1, 16384, 320, 50.0, 0.1), (2, 4096, 640, -200.0, 0.5), (1, 1024, 1280, 1000.0, 1.0)])
+def test_group_norm_large_mean(ctx, B, HW, C, mean, std):
+    """|mean| / sigma up to 1000 (real SDXL activations have groups like this): the variance must come from centred sums
+    (reference groupnorm/mod.rs:75-82 centres first), not from E[x^2] - mean^2 in f32."""
+    g = torch.Generator().manual_seed(HW + C)
+    x = torch.randn(B, HW, C, generator=g) * std + mean
+    x += torch.linspace(-3 * std, 3 * std, C)[None, None, :]     # per-channel offsets inside a group
+    gamma = 1 + 0.1 * torch.randn(C, generator=g)
+    beta = 0.1 * torch.randn(C, generator=g)
+    ref = O.group_norm(x.double().permute(0, 2, 1).reshape(B, C, HW, 1), gamma.double(), beta.double()).reshape(B, C, HW).permute(0, 2, 1)
+    out = ctx.group_norm(x, None, gamma, beta, silu=False)
+    e = rel_err(out, ref)
+    print(f"group_norm mean {mean} std {std}: rel err {e:.3e}")
+    assert e < 1e-3   # f32 input quantisation of (x - mean) alone is ~|mean| 2^-24 / std
+
+
 @pytest.mark.parametrize("rows,C", [(1024, 1280), (4096, 640), (100, 128), (33, 256), (7, 64)])
 def test_layer_norm(ctx, rows, C):
     g = torch.Generator().manual_seed(rows + C)
@@ -104,7 +120,10 @@ def test_layer_norm(ctx, rows, C):
 
 @pytest.mark.parametrize("B,T,S,nh", [(1, 256, 256, 2), (2, 1024, 1024, 4), (2, 1024, 77, 20), (1, 4096, 77, 10),
                                       (1, 64, 64, 1), (2, 16, 3, 4), (1, 200, 333, 2), (1, 4096, 4096, 2)])
-def test_qkv_attention(ctx, B, T, S, nh):
+@pytest.mark.parametrize("poly", [0, 1, 2])
+def test_qkv_attention(ctx, B, T, S, nh, poly):
+    """every kernel variant (fraction of the exponentials on the FMA-pipe polynomial: none / a quarter / half)"""
+    ctx.lib.sdxl_dbg_attention_variant(poly)
     g = torch.Generator().manual_seed(T + S + nh)
     C = nh * 64
     q = h16(torch.randn(B, T, C, generator=g))
@@ -112,15 +131,20 @@ def test_qkv_attention(ctx, B, T, S, nh):
     v = h16(torch.randn(B, S, C, generator=g))
     ref = O.qkv_attention(q.float(), k.float(), v.float(), None, nh)
     out = ctx.qkv_attention(q, k, v, None, nh)
+    ctx.lib.sdxl_dbg_attention_variant(-1)
     # P is rounded to f16 before the PV contraction and the output is f16: ~2^-11 relative each
-    assert rel_err(out, ref) < 1.5e-3
+    e = rel_err(out, ref)
+    print(f"attention B={B} T={T} S={S} heads={nh} poly={poly}: rel err {e:.3e}")
+    assert e < 1.0e-3
     assert torch.isfinite(out).all()
 
 
-@pytest.mark.parametrize("scale", [3.0, 6.0])
-def test_qkv_attention_large_dynamic_range(ctx, scale):
-    """Scores whose row maximum jumps by far more than 2^15 between key blocks: exercises the lazy-max overflow
-    fallback (the block is re-run with the exact maximum) and the rescale of the running sums."""
+@pytest.mark.parametrize("poly", [0, 2])
+@pytest.mark.parametrize("scale", [1.5, 3.0, 6.0])
+def test_qkv_attention_large_dynamic_range(ctx, scale, poly):
+    """Scores whose row maximum jumps between key blocks — by a little (lazy reference kept), by more than 2^8 (the row's
+    O accumulator is rescaled in TMEM) and by far more than 2^15 (overflow fallback: the block is re-run with its exact max)."""
+    ctx.lib.sdxl_dbg_attention_variant(poly)
     g = torch.Generator().manual_seed(int(scale * 10))
     B, T, S, nh = 1, 256, 640, 2
     q = h16(torch.randn(B, T, nh * 64, generator=g) * scale)
@@ -129,8 +153,11 @@ def test_qkv_attention_large_dynamic_range(ctx, scale):
     v = h16(torch.randn(B, S, nh * 64, generator=g))
     ref = O.qkv_attention(q.float(), k.float(), v.float(), None, nh)
     out = ctx.qkv_attention(q, k, v, None, nh)
+    ctx.lib.sdxl_dbg_attention_variant(-1)
     assert torch.isfinite(out).all()
-    assert rel_err(out, ref) < 2e-3
+    e = rel_err(out, ref)
+    print(f"attention dynamic range scale {scale} poly {poly}: rel err {e:.3e}")
+    assert e < 2e-3
 
 
 def test_qkv_attention_mask_shape_is_checked(ctx):
@@ -160,31 +187,3 @@ def test_randn_matches_philox_oracle(ctx):
     ref = philox.randn(n, 0x1234_5678_9ABC, 7)
     assert np.abs(out - ref).max() < 1e-4  # identical integer stream; f32 log/sin/cos differ by ulps
     assert abs(out.mean()) < 0.01 and abs(out.std() - 1) < 0.01
-
-
-def test_attention_split_rows_variant_parity():
-    """The experimental two-threads-per-row softmax (SDXL_B200_ATTN_SPLIT=2, read once per process -> subprocess): same bound."""
-    import os
-    import subprocess
-    import sys
-    code = (
-        "import sys, os, torch\n"
-        "sys.path.insert(0, os.path.join(os.getcwd(), 'stable-diffusion-xl-burn_b200')); sys.path.insert(0, os.getcwd())\n"
-        "import sdxl_b200\n"
-        "from oracle import unet_oracle as O\n"
-        "ctx = sdxl_b200.Context(0); g = torch.Generator().manual_seed(0)\n"
-        "worst = 0.0\n"
-        "for (B, T, S, nh) in ((2, 1024, 1024, 4), (1, 300, 77, 2), (1, 256, 640, 3)):\n"
-        "    q = torch.randn(B, T, nh * 64, generator=g).half(); k = torch.randn(B, S, nh * 64, generator=g).half(); v = torch.randn(B, S, nh * 64, generator=g).half()\n"
-        "    out = ctx.qkv_attention(q, k, v, None, nh).float().cpu()\n"
-        "    ref = O.qkv_attention(q.float(), k.float(), v.float(), None, nh)\n"
-        "    worst = max(worst, float((out - ref).norm() / ref.norm()))\n"
-        "print('SPLIT_REL_ERR', worst)\n"
-    )
-    env = dict(os.environ, SDXL_B200_ATTN_SPLIT="2")
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0, r.stderr[-2000:]
-    err = float([ln for ln in r.stdout.splitlines() if ln.startswith("SPLIT_REL_ERR")][0].split()[1])
-    print("split-row attention rel err", err)
-    assert err < 2e-3

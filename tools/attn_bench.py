@@ -1,0 +1,72 @@
+#!/usr/bin/env python
+"""Attention kernel microbenchmark on the UNet's own shapes (SDXL base 1024^2, CFG-batched B=2), per kernel variant.
+
+    python tools/attn_bench.py [out.json]
+
+For each (T, S, heads) of the step and each variant (fraction of exponentials on the FMA pipe: 0, 1/4, 1/2) it reports
+the mean CUDA-event time of `sdxl_qkv_attention` over 20 launches (inputs rotate through 4 buffers; outputs are checked
+against a float32 torch reference on the same device), the algorithmic TFLOP/s (4*B*T*S*C) and the fraction of the
+measured tensor peak. `per_step_ms` weights the shapes by how often one sampler step launches them (60/10/60/10).
+"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "stable-diffusion-xl-burn_b200")):
+    sys.path.insert(0, p)
+
+import torch  # noqa: E402
+import sdxl_b200  # noqa: E402
+
+SHAPES = [  # (T, S, heads, launches per sampler step)
+    (1024, 1024, 20, 60), (4096, 4096, 10, 10), (1024, 77, 20, 60), (4096, 77, 10, 10)]
+
+
+def main():
+    ctx = sdxl_b200.Context(0)
+    lib = ctx.lib
+    res = {"variants": {}}
+    B = 2
+    for poly in (0, 1, 2):
+        lib.sdxl_dbg_attention_variant(poly)
+        rows, per_step = [], 0.0
+        for T, S, nh, count in SHAPES:
+            C = nh * 64
+            g = torch.Generator(device="cuda").manual_seed(T + S + nh)
+            qs = [torch.randn(B, T, C, device="cuda", generator=g).half() for _ in range(4)]
+            ks = [torch.randn(B, S, C, device="cuda", generator=g).half() for _ in range(4)]
+            vs = [torch.randn(B, S, C, device="cuda", generator=g).half() for _ in range(4)]
+            out = ctx.qkv_attention(qs[0], ks[0], vs[0], None, nh)
+            qf, kf, vf = (t.float().reshape(B, -1, nh, 64).transpose(1, 2) for t in (qs[0], ks[0], vs[0]))
+            ref = torch.nn.functional.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2).reshape(B, T, C)
+            err = float((out.float() - ref).norm() / ref.norm())
+            for i in range(3):
+                ctx.qkv_attention(qs[i], ks[i], vs[i], None, nh)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = 20
+            ctx.enter()
+            e0.record(ctx.stream)
+            outs = []
+            for i in range(n):
+                o = torch.empty(B, T, C, device="cuda", dtype=torch.float16)
+                rc = lib.sdxl_qkv_attention(ctx.h, qs[i % 4].data_ptr(), ks[i % 4].data_ptr(), vs[i % 4].data_ptr(), None, B, T, S, C, nh, o.data_ptr())
+                assert rc == 0
+                outs.append(o)
+            e1.record(ctx.stream)
+            ctx.synchronize()
+            us = e0.elapsed_time(e1) * 1e3 / n
+            fl = 4.0 * B * T * S * C
+            rows.append({"T": T, "S": S, "heads": nh, "us": round(us, 2), "tflops": round(fl / us * 1e-6, 1), "rel_err_vs_f32": err})
+            per_step += us * count * 1e-3
+        res["variants"][f"poly{poly}"] = {"shapes": rows, "per_step_ms": round(per_step, 3)}
+        print(f"poly{poly}: per-step attention {per_step:.3f} ms :: " + " | ".join(f"T{r['T']} S{r['S']}: {r['us']} us ({r['tflops']} TF/s, err {r['rel_err_vs_f32']:.1e})" for r in rows), flush=True)
+    lib.sdxl_dbg_attention_variant(-1)
+    if len(sys.argv) > 1:
+        with open(sys.argv[1], "w") as fh:
+            json.dump(res, fh, indent=1)
+
+
+if __name__ == "__main__":
+    main()
