@@ -12,9 +12,12 @@
 // uniform overflow-safe redo), and the rare re-base rescales the row's O in TMEM in place. The CTA is persistent over a
 // contiguous range of (batch, head, query tile) work items and all barriers run with continuous phases, so the Q load, first
 // Q K^T and the output write-back of consecutive items overlap (no drain / re-initialisation between items).
-// The exp work (MUFU ex2 + the f32->f16 pack, both on the XU pipe) is what bounds d = 64 attention, so a compile-time
-// fraction of the exponentials is evaluated on the FMA pipe instead (Cody-Waite range reduction + degree-4 polynomial,
-// max relative error 3e-6, far below the f16 rounding of P).
+// The XU pipe (16 lanes / clk / SM) bounds d = 64 attention: it executes the MUFU ex2 AND the F2FP f32->f16 pack. Two
+// compile-time levers move work off it (measured in profiles/): PACK = 1 builds the f16 pairs with integer ops instead of
+// F2FP (p * 2^-112 aligns the f32 exponent field with f16's, including f16 subnormals; mantissas are truncated and the row
+// sum is taken over the truncated values, so numerator and denominator stay consistent and the error is zero-mean with the
+// same spread as round-to-nearest); POLY evaluates a fraction of the exponentials on the FMA pipe (Cody-Waite range
+// reduction + degree-4 polynomial, max relative error 3e-6, far below the f16 rounding of P).
 // Warp roles (320 threads): warp0 TMA producer, warp1 MMA issuer + TMEM owner, warps 2..5 softmax A, 6..9 softmax B.
 // TMEM columns: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384) P_A [384,448) P_B [448,512).
 #include <stdlib.h>
@@ -138,8 +141,9 @@ __device__ __forceinline__ void mma_pv(uint32_t d_tmem, uint32_t p_tmem, uint32_
 }
 
 // One 32-column chunk of a score row: p = 2^(s*c - mb) -> packed f16 (16 words); tracks the row's block max (two chains) and
-// the f32 sum. POLY = 0: every exponential on the MUFU; 1: every 4th on the FMA pipe; 2: every 2nd.
-template <int POLY>
+// the f32 sum. POLY = 0: every exponential on the MUFU; 1: every 4th on the FMA pipe; 2: every 2nd. PACK = 0: F2FP round-to-
+// nearest pack; 1: integer truncating pack (see the header).
+template <int POLY, int PACK>
 __device__ __forceinline__ void softmax_chunk(const uint32_t (&v)[32], uint32_t (&h)[16], float sl2e, float mb, float& b0, float& b1,
                                               float& sum, bool ragged, int col0, int S) {
   float s_a = 0.f, s_b = 0.f;
@@ -153,18 +157,28 @@ __device__ __forceinline__ void softmax_chunk(const uint32_t (&v)[32], uint32_t 
     b0 = fmaxf(b0, s0);
     b1 = fmaxf(b1, s1);
     const float x0 = fmaf(s0, sl2e, -mb), x1 = fmaf(s1, sl2e, -mb);
-    const float p0 = ex2_approx(x0);
+    float p0 = ex2_approx(x0);
     const bool poly1 = (POLY == 2) || (POLY == 1 && (i & 2));
-    const float p1 = poly1 ? ex2_poly(x1) : ex2_approx(x1);
-    s_a += p0;
-    s_b += p1;
-    __half2 t = __floats2half2_rn(p0, p1);
-    h[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
+    float p1 = poly1 ? ex2_poly(x1) : ex2_approx(x1);
+    if constexpr (PACK == 0) {
+      s_a += p0;
+      s_b += p1;
+      __half2 t = __floats2half2_rn(p0, p1);
+      h[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
+    } else {
+      p0 = __uint_as_float(__float_as_uint(p0) & 0xFFFFE000u);   // 11 significant bits, towards zero
+      p1 = __uint_as_float(__float_as_uint(p1) & 0xFFFFE000u);
+      s_a += p0;
+      s_b += p1;
+      const uint32_t u0 = __float_as_uint(p0 * 1.925929944387236e-34f);   // * 2^-112: f32 exponent field == f16 exponent field
+      const uint32_t u1 = __float_as_uint(p1 * 1.925929944387236e-34f);   //   (gradual underflow included); low 13 bits stay 0
+      h[i >> 1] = (u1 << 3) + (u0 >> 13);
+    }
   }
   sum += s_a + s_b;
 }
 
-template <int POLY>
+template <int POLY, int PACK>
 __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;                                  // [kQSlots]
@@ -177,10 +191,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
   uint64_t* kv_empty = kv_full + kKvStages;      // [3]
   uint64_t* s_full = kv_empty + kKvStages;       // [2] per slot
   uint64_t* p_full = s_full + 2;                 // [2] per slot, 128 arrivals
-  uint64_t* o_full = p_full + 2;                 // [2] per slot
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* o_full = p_full + 2;                 // [2] per slot: last P V of an item retired
+  uint64_t* pv_done = o_full + 2;                // [2] per slot: P V of the block retired (O may be rescaled, P rewritten)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_done + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform: role code stays on the uniform datapath
+  const int lane = threadIdx.x & 31;
   const int nblk = (p.S + 127) / 128;
   // Persistent: the (batch, head, 128-query tile) work list is split into contiguous, balanced ranges, one per CTA; inside
   // its range a CTA takes two consecutive tiles of the same head as a two-slot item, a single tile otherwise.
@@ -199,7 +215,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
     tma_prefetch_desc(&p.tmV);
     for (int i = 0; i < kQSlots; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
     for (int i = 0; i < kKvStages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&o_full[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&o_full[i], 1); mbar_init(&pv_done[i], 1); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, 512);
@@ -247,6 +263,13 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
     constexpr uint32_t kTile16 = kTileBytes >> 4;
     uint32_t qf_ph = 0, pf_ph = 0;
     int kvc = 0, item = 0;
+    int dn = 0;
+    const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && lane == 0;
+    // Issue order (one in-order tensor pipe, two slots): slot B runs HALF A PERIOD behind slot A, so one slot's exp phase
+    // (the XU-bound part) covers the other slot's hand-over + MMA latency. The stagger is created once per item — S_B(0) is
+    // issued only when slot A hands over its first P — and is self-sustaining afterwards. Per hand-over of slot X at block j:
+    // S_X(j+1) = Q_X K_{j+1}^T goes FIRST (it is what the softmax warps wait for; S_X(j) is dead once P_X(j) exists), then
+    // O_X += P_X(j) V_j.
     for (int tile = t_begin; tile < t_end; ++item) {
       const int qt = tile % nqt;
       const bool hasB = (qt + 1 < nqt) && (tile + 1 < t_end);
@@ -254,48 +277,54 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
       const int qs0 = (item & 1) * 2;
       mbar_wait(&q_full[qs0], (qf_ph >> qs0) & 1u);
       qf_ph ^= 1u << qs0;
-      if (hasB) {
-        mbar_wait(&q_full[qs0 + 1], (qf_ph >> (qs0 + 1)) & 1u);
-        qf_ph ^= 1u << (qs0 + 1);
-      }
       int st = kvc % kKvStages;
       mbar_wait(&kv_full[st], (kvc / kKvStages) & 1);
       tc_fence_after();
       mma_qk_commit(tmem_base + kColS, q_lo0 + qs0 * kTile16, k_lo0 + st * kTile16, dhi, idesc_qk, &s_full[0]);
-      if (hasB) mma_qk_commit(tmem_base + kColS + 128, q_lo0 + (qs0 + 1) * kTile16, k_lo0 + st * kTile16, dhi, idesc_qk, &s_full[1]);
+      if (hasB) {
+        mbar_wait(&q_full[qs0 + 1], (qf_ph >> (qs0 + 1)) & 1u);
+        qf_ph ^= 1u << (qs0 + 1);
+      }
       for (int j = 0; j < nblk; ++j, ++kvc) {
         const bool more = j + 1 < nblk;
         st = kvc % kKvStages;
         const int stn = (kvc + 1) % kKvStages;
-        // ---- slot A: O_A (+)= P_A V_j, then S_A = Q_A K_{j+1}^T
+        // ---- slot A hands over P_A(j)
         mbar_wait(&p_full[0], pf_ph & 1u);
         pf_ph ^= 1u;
+        if (dbg && dn < 256) p.dbg[2048 + dn * 4 + 0] = clock64();
         tc_fence_after();
-        mma_pv(tmem_base + kColO, tmem_base + kColP, v_lo0 + st * kTile16, dhi, idesc_pv, j > 0 ? 1u : 0u);
+        if (j == 0 && hasB)   // start of slot B, half a period behind A
+          mma_qk_commit(tmem_base + kColS + 128, q_lo0 + (qs0 + 1) * kTile16, k_lo0 + st * kTile16, dhi, idesc_qk, &s_full[1]);
         if (more) {
           mbar_wait(&kv_full[stn], ((kvc + 1) / kKvStages) & 1);
           tc_fence_after();
           mma_qk_commit(tmem_base + kColS, q_lo0 + qs0 * kTile16, k_lo0 + stn * kTile16, dhi, idesc_qk, &s_full[0]);
-        } else {
+        }
+        mma_pv(tmem_base + kColO, tmem_base + kColP, v_lo0 + st * kTile16, dhi, idesc_pv, j > 0 ? 1u : 0u);
+        tc_commit_elect(&pv_done[0]);
+        if (!more) {
           tc_commit_elect(&o_full[0]);
           tc_commit_elect(&q_empty[qs0]);
         }
-        // ---- slot B
+        if (dbg && dn < 256) p.dbg[2048 + dn * 4 + 1] = clock64();
+        // ---- slot B hands over P_B(j)
         if (hasB) {
           mbar_wait(&p_full[1], (pf_ph >> 1) & 1u);
           pf_ph ^= 2u;
+          if (dbg && dn < 256) p.dbg[2048 + dn * 4 + 2] = clock64();
           tc_fence_after();
+          if (more) mma_qk_commit(tmem_base + kColS + 128, q_lo0 + (qs0 + 1) * kTile16, k_lo0 + stn * kTile16, dhi, idesc_qk, &s_full[1]);
           mma_pv(tmem_base + kColO + 64, tmem_base + kColP + 64, v_lo0 + st * kTile16, dhi, idesc_pv, j > 0 ? 1u : 0u);
-        }
-        tc_commit_elect(&kv_empty[st]);   // K_j / V_j are free once everything issued so far retires
-        if (hasB) {
-          if (more) {
-            mma_qk_commit(tmem_base + kColS + 128, q_lo0 + (qs0 + 1) * kTile16, k_lo0 + stn * kTile16, dhi, idesc_qk, &s_full[1]);
-          } else {
+          tc_commit_elect(&pv_done[1]);
+          if (!more) {
             tc_commit_elect(&o_full[1]);
             tc_commit_elect(&q_empty[qs0 + 1]);
           }
         }
+        tc_commit_elect(&kv_empty[st]);   // K_j / V_j are free once everything issued so far retires
+        if (dbg && dn < 256) p.dbg[2048 + dn * 4 + 3] = clock64();
+        ++dn;
       }
     }
   } else {
@@ -308,7 +337,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
     const uint32_t tO = tmem_base + lane_off + kColO + x * 64;
     const uint32_t tP = tmem_base + lane_off + kColP + x * 64;
     const float sl2e = p.scale_log2e;
-    uint32_t s_ph = 0, o_ph = 0;
+    uint32_t s_ph = 0, o_ph = 0, d_ph = 0;
+    bool pv_any = false;
+    int dn = 0;
+    const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && q == 0 && lane == 0;
     for (int tile = t_begin; tile < t_end;) {
       const int qt = tile % nqt, head = (tile / nqt) % p.n_head, b = tile / (nqt * p.n_head);
       const bool hasB = (qt + 1 < nqt) && (tile + 1 < t_end);
@@ -316,8 +348,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
       if (x == 1 && !hasB) continue;
       float m = -INFINITY, m_prev = -INFINITY, l = 0.f;
       for (int j = 0; j < nblk; ++j) {
-        mbar_wait(&s_full[x], s_ph);   // S(j) complete; it was issued after P V of block j-1, so O(j-1) is complete too
+        mbar_wait(&s_full[x], s_ph);   // S(j) complete
         s_ph ^= 1u;
+        if (dbg && dn < 256) p.dbg[x * 1024 + dn * 4 + 0] = clock64();
         tc_fence_after();
         const int kbase = j * 128;
         const bool ragged = kbase + 128 > p.S;
@@ -344,6 +377,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         }
         float sum, bmax;
         bool redo;
+        bool pv_pending = pv_any;   // a P V of this slot was issued before this block
+        pv_any = true;
         do {
           const float mb = ref * sl2e;
           sum = 0.f;
@@ -353,20 +388,31 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
           tmem_ld32(tS, va);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
+            if (dbg && x == 0 && dn < 32) p.dbg[3072 + dn * 16 + c * 3 + 0] = clock64();
             tmem_ld_wait();
+            if (dbg && x == 0 && dn < 32) p.dbg[3072 + dn * 16 + c * 3 + 1] = clock64();
             const bool live = kbase + c * 32 < p.S;          // warp-uniform: chunk has at least one valid key
             const bool next_live = c < 3 && kbase + (c + 1) * 32 < p.S;
             if (c & 1) {
               if (next_live) tmem_ld32(tS + (c + 1) * 32, va);
-              if (live) softmax_chunk<POLY>(vb, h, sl2e, mb, b0, b1, sum, ragged, kbase + c * 32, p.S);
+              if (live) softmax_chunk<POLY, PACK>(vb, h, sl2e, mb, b0, b1, sum, ragged, kbase + c * 32, p.S);
             } else {
               if (next_live) tmem_ld32(tS + (c + 1) * 32, vb);
-              if (live) softmax_chunk<POLY>(va, h, sl2e, mb, b0, b1, sum, ragged, kbase + c * 32, p.S);
+              if (live) softmax_chunk<POLY, PACK>(va, h, sl2e, mb, b0, b1, sum, ragged, kbase + c * 32, p.S);
             }
             if (!live) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) h[i] = 0u;
             }
+            if (c == 0 && pv_pending) {
+              // The previous P V of this slot (issued right after this block's Q K^T) still reads P and writes O: it must have
+              // retired before P is overwritten / O is rescaled. One exp chunk later it practically always has.
+              mbar_wait(&pv_done[x], d_ph);
+              d_ph ^= 1u;
+              tc_fence_after();
+              pv_pending = false;
+            }
+            if (dbg && x == 0 && dn < 32) p.dbg[3072 + dn * 16 + c * 3 + 2] = clock64();
             tmem_st16(tP + c * 16, h);
           }
           bmax = fmaxf(b0, b1);
@@ -376,8 +422,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
           if (over) ref = bmax;
           if (redo) tmem_st_wait();
         } while (redo);
+        if (dbg && dn < 256) p.dbg[x * 1024 + dn * 4 + 1] = clock64();
         if (j > 0) {
-          // the row's reference moved: rescale what has been accumulated so far (rare; O(j-1) is complete, see above)
+          // the row's reference moved: rescale what has been accumulated so far (rare; O(j-1) is complete: pv_done above)
           const bool moved = ref != m_prev;
           if (__any_sync(0xffffffffu, moved)) {
             const float alpha = moved ? ex2_approx((m_prev - ref) * sl2e) : 1.0f;
@@ -399,6 +446,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&p_full[x]);
+        if (dbg && dn < 256) p.dbg[x * 1024 + dn * 4 + 2] = clock64();
+        ++dn;
       }
       // ---- write-back: O / l -> f16 (the next item's Q K^T and first exp phase overlap this)
       mbar_wait(&o_full[x], o_ph);
@@ -426,6 +475,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         }
       }
       tc_fence_before();   // the TMEM reads above are ordered before this thread's next p_full arrival
+      if (dbg && dn <= 256) p.dbg[x * 1024 + (dn - 1) * 4 + 3] = clock64();   // write-back of this item done
     }
   }
 
@@ -439,8 +489,21 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
 // is a per-device function attribute).
 struct AttnDev { bool attr = false; int num_sms = 0; };
 static AttnDev g_attn_dev[64];
-static int g_attn_poly = -1;   // -1: default; sdxl_dbg_attention_variant sets 0 / 1 / 2
-void attention_set_variant(int poly) { g_attn_poly = poly; }
+static int g_attn_variant = -1;   // -1: default; sdxl_dbg_attention_variant sets POLY + 4 * PACK
+void attention_set_variant(int v) { g_attn_variant = v; }
+
+typedef void (*AttnKernel)(const AttnParams);
+static AttnKernel attn_kernel_for(int v) {
+  switch (v) {
+    case 0: return attention_kernel<0, 0>;
+    case 1: return attention_kernel<1, 0>;
+    case 2: return attention_kernel<2, 0>;
+    case 4: return attention_kernel<0, 1>;
+    case 5: return attention_kernel<1, 1>;
+    case 6: return attention_kernel<2, 1>;
+    default: return nullptr;
+  }
+}
 
 int attention_launch(cudaStream_t st, const AttnParams& p) {
   int dev = 0;
@@ -449,22 +512,22 @@ int attention_launch(cudaStream_t st, const AttnParams& p) {
   if (dev < 0 || dev >= 64) return 2001;
   AttnDev& D = g_attn_dev[dev];
   if (!D.attr) {
-    e = cudaFuncSetAttribute(attention_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
-    if (e != cudaSuccess) return (int)e;
+    for (int v = 0; v < 8; ++v)
+      if (attn_kernel_for(v)) {
+        e = cudaFuncSetAttribute(attn_kernel_for(v), cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+        if (e != cudaSuccess) return (int)e;
+      }
     cudaDeviceGetAttribute(&D.num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (D.num_sms <= 0) D.num_sms = 148;
     D.attr = true;
   }
-  static const int env_poly = getenv("SDXL_B200_ATTN_POLY") ? atoi(getenv("SDXL_B200_ATTN_POLY")) : 1;
-  const int poly = g_attn_poly >= 0 ? g_attn_poly : env_poly;
+  static const int env_variant = getenv("SDXL_B200_ATTN_VARIANT") ? atoi(getenv("SDXL_B200_ATTN_VARIANT")) : 4;
+  AttnKernel k = attn_kernel_for(g_attn_variant >= 0 ? g_attn_variant : env_variant);
+  if (!k) k = attn_kernel_for(4);
   const long tiles = (long)p.B * p.n_head * ((p.T + 127) / 128);
   const long want = (tiles + 1) / 2;  // one two-slot item per CTA when the machine is not full
   dim3 grid((unsigned)(want < D.num_sms ? (want > 0 ? want : 1) : D.num_sms));
-  if (poly == 0) return launch_kernel(attention_kernel<0>, grid, dim3(kAttnThreads), (size_t)kAttnSmem, st, true, p);
-  if (poly == 2) return launch_kernel(attention_kernel<2>, grid, dim3(kAttnThreads), (size_t)kAttnSmem, st, true, p);
-  return launch_kernel(attention_kernel<1>, grid, dim3(kAttnThreads), (size_t)kAttnSmem, st, true, p);
+  return launch_kernel(k, grid, dim3(kAttnThreads), (size_t)kAttnSmem, st, true, p);
 }
 
 }  // namespace sdxl

@@ -208,39 +208,39 @@ __device__ __forceinline__ void tc_mma_f16_pair_elect(uint32_t d_tmem, uint32_t 
 // under a single elect.sync: the issue loop's cost per K block is what bounds the GEMM main loop.
 // `acc_first` = accumulate flag of the first MMA (0 only for the first K block of a tile).
 __device__ __forceinline__ void tc_mma4_commit_pair_elect(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
-                                                          uint32_t idesc, uint32_t acc_first, uint64_t* bar, uint32_t do_mma) {
+                                                          uint32_t idesc, uint32_t acc_first, uint64_t* bar) {
+  // every instruction is predicated on the elect result ONLY: ptxas then keeps the whole sequence on the uniform datapath
+  // (UTCHMMA with UR operands back to back); mixing further conditions into the predicate brings back a per-MMA
+  // ELECT / R2UR.BROADCAST waterfall loop.
   asm volatile(
       "{\n\t"
-      ".reg .pred p, e, m, t;\n\t"
+      ".reg .pred p, e, t;\n\t"
       ".reg .b64 da, db;\n\t"
       ".reg .b32 al, bl;\n\t"
       "elect.sync _|e, 0xffffffff;\n\t"
       "setp.ne.b32 p, %5, 0;\n\t"
-      "setp.ne.b32 m, %7, 0;\n\t"
-      "and.pred m, m, e;\n\t"
       "setp.eq.b32 t, 0, 0;\n\t"
       "mov.b64 da, {%1, %3};\n\t"
       "mov.b64 db, {%2, %3};\n\t"
-      "@m tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t"
       "add.u32 al, %1, 2;\n\t"
       "add.u32 bl, %2, 2;\n\t"
       "mov.b64 da, {al, %3};\n\t"
       "mov.b64 db, {bl, %3};\n\t"
-      "@m tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, t;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, t;\n\t"
       "add.u32 al, %1, 4;\n\t"
       "add.u32 bl, %2, 4;\n\t"
       "mov.b64 da, {al, %3};\n\t"
       "mov.b64 db, {bl, %3};\n\t"
-      "@m tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, t;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, t;\n\t"
       "add.u32 al, %1, 6;\n\t"
       "add.u32 bl, %2, 6;\n\t"
       "mov.b64 da, {al, %3};\n\t"
       "mov.b64 db, {bl, %3};\n\t"
-      "@m tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, t;\n\t"
-      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%6], %8;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, t;\n\t"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%6], %7;\n\t"
       "}"
-      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(acc_first), "r"(smem_u32(bar)), "r"(do_mma),
-        "h"((uint16_t)3)
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(acc_first), "r"(smem_u32(bar)), "h"((uint16_t)3)
       : "memory");
 }
 __device__ __forceinline__ void tc_commit_elect(uint64_t* bar) {

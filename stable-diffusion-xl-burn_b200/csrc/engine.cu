@@ -1159,6 +1159,40 @@ extern "C" int sdxl_op_timestep_embedding(sdxl_ctx* c, const int32_t* t_host, in
 // -1 restores the default). Process-wide; used by tools/attn_bench.py and the parity tests to cover every variant.
 extern "C" void sdxl_dbg_attention_variant(int poly) { attention_set_variant(poly); }
 
+// Diagnostics: clock64 stamps of CTA 0 of one attention launch on synthetic data (tools/attn_timeline.py).
+// stamps_host[4][1024]: [3][dn < 32][16] = slot A per chunk {before ld wait, after ld wait, after exp} x 4; [0..2][256][4]: role 0/1 = softmax slot A/B (one warp's lane 0): {S ready, exp phase done, P handed over, item written
+// back}; role 2 = MMA issuer: {P_A ready, P V_A + Q K_A issued, P_B ready, P V_B + Q K_B issued}; per key block, in clocks.
+extern "C" int sdxl_dbg_attention_timeline(sdxl_ctx* c, int B, int T, int S, int n_head, long long* stamps_host) {
+  if (!c || !stamps_host) return -1;
+  CU(c, cudaSetDevice(c->device));
+  TmpBufs Tm(c->stream);
+  const int C = n_head * 64;
+  __half* q = (__half*)Tm.get((size_t)B * T * C * 2);
+  __half* k = (__half*)Tm.get((size_t)B * S * C * 2);
+  __half* v = (__half*)Tm.get((size_t)B * S * C * 2);
+  __half* o = (__half*)Tm.get((size_t)B * T * C * 2);
+  long long* dbg = (long long*)Tm.get(4 * 1024 * 8);
+  if (!q || !k || !v || !o || !dbg) return fail(c, 5400, "temporary allocation failed");
+  CU(c, cudaMemsetAsync(q, 0, (size_t)B * T * C * 2, c->stream));
+  CU(c, cudaMemsetAsync(k, 0, (size_t)B * S * C * 2, c->stream));
+  CU(c, cudaMemsetAsync(v, 0, (size_t)B * S * C * 2, c->stream));
+  CU(c, cudaMemsetAsync(dbg, 0, 4 * 1024 * 8, c->stream));
+  AttnParams p{};
+  p.T = T; p.S = S; p.n_head = n_head; p.B = B;
+  p.out = o; p.ldo = C;
+  p.scale_log2e = (float)(1.4426950408889634 / sqrt(64.0));
+  int r = make_tmap_rows(&p.tmQ, q, T, B, C, C);
+  if (!r) r = make_tmap_rows(&p.tmK, k, S, B, C, C);
+  if (!r) r = make_tmap_rows(&p.tmV, v, S, B, C, C);
+  if (r) return fail(c, r, "tensor map creation failed");
+  for (int i = 0; i < 3; ++i) KL(c, attention_launch(c->stream, p));
+  p.dbg = dbg;
+  KL(c, attention_launch(c->stream, p));
+  CU(c, cudaMemcpyAsync(stamps_host, dbg, 4 * 1024 * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 // Diagnostics: in-kernel timeline (%globaltimer, ns) of CTA 0 of one igemm launch on a synthetic [M,K]x[K,N] problem.
 // stamps_host[0..6] = prologue done, dependencies resolved, first operands landed, first accumulator complete,
 // first epilogue done, producer done, all roles done; stamps_host[7] = CUDA-event duration of the launch in ns.

@@ -484,10 +484,10 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* epi_stage = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tmem_ptr) + 16);  // [kEpiWarps][32][36] f32
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform: role loops stay on the uniform datapath
   const int lane = threadIdx.x & 31;
   const int CM = p.CM, CN = p.CN, cs = CM * CN;
-  const int rank = cs > 1 ? (int)cluster_ctarank() : 0;
+  const int rank = (int)(blockIdx.x % (unsigned)cs);   // == %cluster_ctarank for 1-D clusters; blockIdx keeps it on the uniform datapath
   const int cm_idx = rank % CM, cn_idx = rank / CM;
   const int m_tiles = p.tilesW * p.tilesH * p.tilesB;
   const int m_super = (m_tiles + CM - 1) / CM, n_super = (p.tilesN + CN - 1) / CN;
@@ -745,9 +745,9 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_pair_kernel(const __grid_co
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* epi_stage = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tmem_ptr) + 16);  // [kEpiWarps][32][36] f32
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform: role loops stay on the uniform datapath
   const int lane = threadIdx.x & 31;
-  const int rank = (int)cluster_ctarank();  // 0 = leader
+  const int rank = (int)(blockIdx.x & 1u);  // == %cluster_ctarank for the (2,1,1) cluster; 0 = leader. blockIdx keeps it on the uniform datapath
   const int m_tiles = p.tilesW * p.tilesH * p.tilesB;
   const int pm_tiles = m_tiles >> 1;
   const int num_ptiles = pm_tiles * p.tilesN;
@@ -847,8 +847,8 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_pair_kernel(const __grid_co
           {
             const uint32_t a_lo = a_lo0 + stage * stage_inc, b_lo = a_lo + b_off;
             // four MMAs + the commit that frees the slot in both CTAs, one elect
-            tc_mma4_commit_pair_elect(d_tmem, a_lo, b_lo, desc_hi, idesc, kb > 0 ? 1u : 0u, &empty_bar[stage],
-                                      p.dbg_mode != 2 ? 1u : 0u);
+            if (p.dbg_mode != 2) tc_mma4_commit_pair_elect(d_tmem, a_lo, b_lo, desc_hi, idesc, kb > 0 ? 1u : 0u, &empty_bar[stage]);
+            else tc_commit_pair_elect(&empty_bar[stage]);   // diagnostics: loads and barriers only
           }
           if (++stage == (uint32_t)nst) { stage = 0; phase ^= 1; }
         }

@@ -141,11 +141,12 @@ struct AttnParams {
   __half* out;                 // [B*T, ldo]
   int ldo;
   float scale_log2e;           // (1/sqrt(d)) * log2(e)
+  long long* dbg;              // nullable: clock64 stamps of CTA 0 (sdxl_dbg_attention_timeline)
 };
 int make_tmap_rows(CUtensorMap* tm, const __half* base, int rows_per_batch, int nbatch, int cols, int pitch);
 int attention_launch(cudaStream_t st, const AttnParams& p);
-// diagnostics: fraction of the exponentials evaluated on the FMA pipe (0: none, 1: 1/4, 2: 1/2; -1: default / SDXL_B200_ATTN_POLY)
-void attention_set_variant(int poly);
+// diagnostics: kernel variant = POLY + 4 * PACK (attention.cu); -1: default / SDXL_B200_ATTN_VARIANT
+void attention_set_variant(int v);
 
 // ------------------------------------------------------------------------------------------------
 // Norms (norm.cu)

@@ -120,9 +120,9 @@ def test_layer_norm(ctx, rows, C):
 
 @pytest.mark.parametrize("B,T,S,nh", [(1, 256, 256, 2), (2, 1024, 1024, 4), (2, 1024, 77, 20), (1, 4096, 77, 10),
                                       (1, 64, 64, 1), (2, 16, 3, 4), (1, 200, 333, 2), (1, 4096, 4096, 2)])
-@pytest.mark.parametrize("poly", [0, 1, 2])
+@pytest.mark.parametrize("poly", [0, 2, 4, 5])
 def test_qkv_attention(ctx, B, T, S, nh, poly):
-    """every kernel variant (fraction of the exponentials on the FMA-pipe polynomial: none / a quarter / half)"""
+    """kernel variants POLY + 4 * PACK (csrc/attention.cu): MUFU / FMA-pipe exponentials, F2FP / integer truncating pack of P"""
     ctx.lib.sdxl_dbg_attention_variant(poly)
     g = torch.Generator().manual_seed(T + S + nh)
     C = nh * 64
@@ -139,7 +139,7 @@ def test_qkv_attention(ctx, B, T, S, nh, poly):
     assert torch.isfinite(out).all()
 
 
-@pytest.mark.parametrize("poly", [0, 2])
+@pytest.mark.parametrize("poly", [0, 4, 6])
 @pytest.mark.parametrize("scale", [1.5, 3.0, 6.0])
 def test_qkv_attention_large_dynamic_range(ctx, scale, poly):
     """Scores whose row maximum jumps between key blocks — by a little (lazy reference kept), by more than 2^8 (the row's

@@ -19,6 +19,7 @@ for p in (ROOT, os.path.join(ROOT, "stable-diffusion-xl-burn_b200")):
 import torch  # noqa: E402
 import sdxl_b200  # noqa: E402
 
+VARIANTS = (0, 4, 5, 6)   # POLY + 4 * PACK (csrc/attention.cu)
 SHAPES = [  # (T, S, heads, launches per sampler step)
     (1024, 1024, 20, 60), (4096, 4096, 10, 10), (1024, 77, 20, 60), (4096, 77, 10, 10)]
 
@@ -28,7 +29,7 @@ def main():
     lib = ctx.lib
     res = {"variants": {}}
     B = 2
-    for poly in (0, 1, 2):
+    for poly in VARIANTS:
         lib.sdxl_dbg_attention_variant(poly)
         rows, per_step = [], 0.0
         for T, S, nh, count in SHAPES:
@@ -60,8 +61,8 @@ def main():
             fl = 4.0 * B * T * S * C
             rows.append({"T": T, "S": S, "heads": nh, "us": round(us, 2), "tflops": round(fl / us * 1e-6, 1), "rel_err_vs_f32": err})
             per_step += us * count * 1e-3
-        res["variants"][f"poly{poly}"] = {"shapes": rows, "per_step_ms": round(per_step, 3)}
-        print(f"poly{poly}: per-step attention {per_step:.3f} ms :: " + " | ".join(f"T{r['T']} S{r['S']}: {r['us']} us ({r['tflops']} TF/s, err {r['rel_err_vs_f32']:.1e})" for r in rows), flush=True)
+        res["variants"][f"variant{poly}"] = {"shapes": rows, "per_step_ms": round(per_step, 3)}
+        print(f"variant {poly}: per-step attention {per_step:.3f} ms :: " + " | ".join(f"T{r['T']} S{r['S']}: {r['us']} us ({r['tflops']} TF/s, err {r['rel_err_vs_f32']:.1e})" for r in rows), flush=True)
     lib.sdxl_dbg_attention_variant(-1)
     if len(sys.argv) > 1:
         with open(sys.argv[1], "w") as fh:
