@@ -158,10 +158,6 @@ SDXL_API int sdxl_unet_profile_dump(sdxl_unet* unet, const char* path_host);
  * [M,K]x[K,N] problem; stamps_host[9]: see csrc/engine.cu. */
 SDXL_API int sdxl_dbg_igemm_timeline(sdxl_ctx* ctx, int M, int K, int N, int geglu, int with_residual,
                                      uint64_t* stamps_host);
-/* Diagnostics: attention kernel variant = POLY + 4 * PACK. POLY: fraction of the softmax exponentials evaluated on the FMA
- * pipe instead of the MUFU (0 none, 1 a quarter, 2 half); PACK: 0 = F2FP round-to-nearest f16 pack of P, 1 = integer
- * truncating pack with a consistent row sum. -1 = default. Process-wide. */
-SDXL_API void sdxl_dbg_attention_variant(int variant);
 /* Diagnostics: clock stamps of CTA 0 of one attention launch on synthetic data; stamps_host[3][256][4] (csrc/engine.cu). */
 SDXL_API int sdxl_dbg_attention_timeline(sdxl_ctx* ctx, int B, int T, int S, int n_head, long long* stamps_host);
 /* seeded N(0,1) exactly as the sampler generates it (device out). */

@@ -12,13 +12,14 @@
 // uniform overflow-safe redo), and the rare re-base rescales the row's O in TMEM in place. The CTA is persistent over a
 // contiguous range of (batch, head, query tile) work items and all barriers run with continuous phases, so the Q load, first
 // Q K^T and the output write-back of consecutive items overlap (no drain / re-initialisation between items).
-// The XU pipe (16 lanes / clk / SM) bounds d = 64 attention: it executes the MUFU ex2 AND the F2FP f32->f16 pack. Two
-// compile-time levers move work off it (measured in profiles/): PACK = 1 builds the f16 pairs with integer ops instead of
-// F2FP (p * 2^-112 aligns the f32 exponent field with f16's, including f16 subnormals; mantissas are truncated and the row
-// sum is taken over the truncated values, so numerator and denominator stay consistent and the error is zero-mean with the
-// same spread as round-to-nearest); POLY evaluates a fraction of the exponentials on the FMA pipe (Cody-Waite range
-// reduction + degree-4 polynomial, max relative error 3e-6, far below the f16 rounding of P).
-// Warp roles (320 threads): warp0 TMA producer, warp1 MMA issuer + TMEM owner, warps 2..5 softmax A, 6..9 softmax B.
+// What bounds d = 64 attention is the XU pipe (16 lanes / clk / SM): it executes both the MUFU ex2 and the F2FP f32->f16 pack
+// of P (1.5 XU instructions per score vs 4 clk of tensor time per 128 scores and row). ONE warp per scheduler cannot keep
+// that pipe busy (in-order issue, ~500 clk per 32-column chunk measured against a 384 clk pipe floor), so every query row is
+// shared by TWO threads (64 score columns each): two warps per scheduler and slot. Measured alternatives that did not pay and
+// were removed (profiles/README.md, round 2): evaluating a fraction of the exponentials on the FMA pipe (Cody-Waite +
+// degree-4 polynomial) and packing P with integer ops instead of F2FP both trade XU time for issue slots one for one.
+// Warp roles (576 threads): warp0 TMA producer, warp1 MMA issuer + TMEM owner, warps 2..9 softmax slot A, 10..17 slot B
+// (warp w of a slot: TMEM lane quarter w % 4, column half (w - 2) / 4 % 2).
 // TMEM columns: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384) P_A [384,448) P_B [448,512).
 #include <stdlib.h>
 
@@ -30,8 +31,8 @@ namespace sdxl {
 static constexpr int kTileBytes = 128 * 128;        // 128 rows x 64 halves (Q, K or V tile)
 static constexpr int kKvStages = 3;
 static constexpr int kQSlots = 4;                   // ring of two items x two slots
-static constexpr int kAttnSmem = kQSlots * kTileBytes + 2 * kKvStages * kTileBytes + 512;
-static constexpr int kAttnThreads = 320;
+static constexpr int kXchgBytes = 2 * 2 * 2 * 128 * 4;   // [buffer][slot][column half][row] f32
+static constexpr int kAttnSmem = kQSlots * kTileBytes + 2 * kKvStages * kTileBytes + 512 + kXchgBytes;
 static constexpr uint32_t kColS = 0, kColO = 256, kColP = 384;
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -39,21 +40,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// 2^x on the FMA / ALU pipes: t = x + 1.5*2^23 rounded towards -inf keeps floor(x) in the low mantissa bits; r = x - floor(x)
-// in [0,1); 2^r by a degree-4 minimax polynomial (max rel. error 3.0e-6); the integer part goes straight into the exponent
-// field. x is clamped at -126 (results below 2^-126 are irrelevant: P is rounded to f16 afterwards).
-__device__ __forceinline__ float ex2_poly(float x) {
-  x = fmaxf(x, -126.0f);
-  float t;
-  asm("add.rm.ftz.f32 %0, %1, 0f4B400000;" : "=f"(t) : "f"(x));
-  const float r = x - (t - 12582912.0f);
-  float p = fmaf(0.013426684f, r, 0.052242474f);
-  p = fmaf(p, r, 0.241280205f);
-  p = fmaf(p, r, 0.693044845f);
-  p = fmaf(p, r, 1.0f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
-
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
@@ -140,10 +126,8 @@ __device__ __forceinline__ void mma_pv(uint32_t d_tmem, uint32_t p_tmem, uint32_
       : "memory");
 }
 
-// One 32-column chunk of a score row: p = 2^(s*c - mb) -> packed f16 (16 words); tracks the row's block max (two chains) and
-// the f32 sum. POLY = 0: every exponential on the MUFU; 1: every 4th on the FMA pipe; 2: every 2nd. PACK = 0: F2FP round-to-
-// nearest pack; 1: integer truncating pack (see the header).
-template <int POLY, int PACK>
+// One 32-column chunk of a score row: p = 2^(s*c - mb) -> packed f16 (16 words); tracks the block max of these columns
+// (two chains) and their f32 sum.
 __device__ __forceinline__ void softmax_chunk(const uint32_t (&v)[32], uint32_t (&h)[16], float sl2e, float mb, float& b0, float& b1,
                                               float& sum, bool ragged, int col0, int S) {
   float s_a = 0.f, s_b = 0.f;
@@ -156,29 +140,19 @@ __device__ __forceinline__ void softmax_chunk(const uint32_t (&v)[32], uint32_t 
     }
     b0 = fmaxf(b0, s0);
     b1 = fmaxf(b1, s1);
-    const float x0 = fmaf(s0, sl2e, -mb), x1 = fmaf(s1, sl2e, -mb);
-    float p0 = ex2_approx(x0);
-    const bool poly1 = (POLY == 2) || (POLY == 1 && (i & 2));
-    float p1 = poly1 ? ex2_poly(x1) : ex2_approx(x1);
-    if constexpr (PACK == 0) {
-      s_a += p0;
-      s_b += p1;
-      __half2 t = __floats2half2_rn(p0, p1);
-      h[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
-    } else {
-      p0 = __uint_as_float(__float_as_uint(p0) & 0xFFFFE000u);   // 11 significant bits, towards zero
-      p1 = __uint_as_float(__float_as_uint(p1) & 0xFFFFE000u);
-      s_a += p0;
-      s_b += p1;
-      const uint32_t u0 = __float_as_uint(p0 * 1.925929944387236e-34f);   // * 2^-112: f32 exponent field == f16 exponent field
-      const uint32_t u1 = __float_as_uint(p1 * 1.925929944387236e-34f);   //   (gradual underflow included); low 13 bits stay 0
-      h[i >> 1] = (u1 << 3) + (u0 >> 13);
-    }
+    const float p0 = ex2_approx(fmaf(s0, sl2e, -mb));
+    const float p1 = ex2_approx(fmaf(s1, sl2e, -mb));
+    s_a += p0;
+    s_b += p1;
+    __half2 t = __floats2half2_rn(p0, p1);
+    h[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
   }
   sum += s_a + s_b;
 }
 
-template <int POLY, int PACK>
+static constexpr int SPLIT = 2;   // threads per query row
+static constexpr int kAttnThreads = 64 + 256 * SPLIT;
+
 __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;                                  // [kQSlots]
@@ -194,6 +168,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
   uint64_t* o_full = p_full + 2;                 // [2] per slot: last P V of an item retired
   uint64_t* pv_done = o_full + 2;                // [2] per slot: P V of the block retired (O may be rescaled, P rewritten)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_done + 2);
+  float* xchg = reinterpret_cast<float*>(sV + kKvStages * kTileBytes + 512);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform: role code stays on the uniform datapath
   const int lane = threadIdx.x & 31;
@@ -215,7 +190,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
     tma_prefetch_desc(&p.tmV);
     for (int i = 0; i < kQSlots; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
     for (int i = 0; i < kKvStages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&o_full[i], 1); mbar_init(&pv_done[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128 * SPLIT); mbar_init(&o_full[i], 1); mbar_init(&pv_done[i], 1); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, 512);
@@ -328,19 +303,34 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
       }
     }
   } else {
-    // ===================== softmax warpgroups: one thread per query row =====================
-    const int x = (warp - 2) >> 2;   // slot: 0 = tile A, 1 = tile B
-    const int q = warp & 3;          // TMEM lane quarter this warp may access (hardware: warp id % 4)
-    const int r = q * 32 + lane;     // query row in the tile == TMEM lane
+    // ===================== softmax warps: two threads per query row =====================
+    // Each thread owns 64 of a key block's 128 score columns (and 32 of the 64 output columns). The two threads of a row agree
+    // on the row's block max (and final sum) through shared memory.
+    constexpr int NCH = 4 / SPLIT;                   // 32-column chunks per thread and key block
+    constexpr int OCOLS = 64 / SPLIT;                // output columns per thread
+    const int sw = warp - 2;
+    const int x = sw / (4 * SPLIT);                  // slot: 0 = tile A, 1 = tile B
+    const int hf = (sw >> 2) & 1;                    // column half
+    const int q = warp & 3;                          // TMEM lane quarter this warp may access (hardware: warp id % 4)
+    const int r = q * 32 + lane;                     // query row in the tile == TMEM lane
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    const uint32_t tS = tmem_base + lane_off + kColS + x * 128;
-    const uint32_t tO = tmem_base + lane_off + kColO + x * 64;
-    const uint32_t tP = tmem_base + lane_off + kColP + x * 64;
+    const uint32_t tS = tmem_base + lane_off + kColS + x * 128 + hf * 64;
+    const uint32_t tO = tmem_base + lane_off + kColO + x * 64 + hf * OCOLS;
+    const uint32_t tP = tmem_base + lane_off + kColP + x * 64 + hf * 32;
     const float sl2e = p.scale_log2e;
     uint32_t s_ph = 0, o_ph = 0, d_ph = 0;
     bool pv_any = false;
-    int dn = 0;
-    const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && q == 0 && lane == 0;
+    int dn = 0, xk = 0;
+    const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && q == 0 && lane == 0 && hf == 0;
+    // max over the row's two halves: double-buffered slots, one 64-thread named barrier per exchange
+    auto exchange_max = [&](float v) -> float {
+      float* slot = xchg + (((xk & 1) * 2 + x) * 2) * 128;
+      slot[hf * 128 + r] = v;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + x * 4 + q) : "memory");
+      const float o = slot[(hf ^ 1) * 128 + r];
+      ++xk;
+      return fmaxf(v, o);
+    };
     for (int tile = t_begin; tile < t_end;) {
       const int qt = tile % nqt, head = (tile / nqt) % p.n_head, b = tile / (nqt * p.n_head);
       const bool hasB = (qt + 1 < nqt) && (tile + 1 < t_end);
@@ -352,15 +342,15 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         s_ph ^= 1u;
         if (dbg && dn < 256) p.dbg[x * 1024 + dn * 4 + 0] = clock64();
         tc_fence_after();
-        const int kbase = j * 128;
-        const bool ragged = kbase + 128 > p.S;
+        const int kbase = j * 128 + hf * 64;         // first key of this thread's columns
+        const bool ragged = j * 128 + 128 > p.S;
         // Exponent reference. Block 0: exact row max (one extra pass over S). Later blocks: the reference decided at the end
         // of the previous block (lazy): p = 2^((s - ref) c) may exceed 1 (f16 P and the f32 sums have the head-room).
         float ref = m;
         if (j == 0) {
           float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll 1
-          for (int c = 0; c < 128; c += 32) {
+          for (int c = 0; c < NCH * 32; c += 32) {
             if (kbase + c >= p.S) break;
             uint32_t v[32];
             tmem_ld32(tS + c, v);
@@ -373,7 +363,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
               if (!ragged || kbase + c + i + 3 < p.S) m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
             }
           }
-          ref = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+          ref = exchange_max(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
         }
         float sum, bmax;
         bool redo;
@@ -383,22 +373,20 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
           const float mb = ref * sl2e;
           sum = 0.f;
           float b0 = -INFINITY, b1 = -INFINITY;
-          // software pipeline over the four 32-column chunks: the TMEM load of chunk c+1 flies while chunk c is exponentiated
+          // software pipeline over the 32-column chunks: the TMEM load of chunk c+1 flies while chunk c is exponentiated
           uint32_t va[32], vb[32], h[16];
           tmem_ld32(tS, va);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            if (dbg && x == 0 && dn < 32) p.dbg[3072 + dn * 16 + c * 3 + 0] = clock64();
+          for (int c = 0; c < NCH; ++c) {
             tmem_ld_wait();
-            if (dbg && x == 0 && dn < 32) p.dbg[3072 + dn * 16 + c * 3 + 1] = clock64();
             const bool live = kbase + c * 32 < p.S;          // warp-uniform: chunk has at least one valid key
-            const bool next_live = c < 3 && kbase + (c + 1) * 32 < p.S;
+            const bool next_live = c < NCH - 1 && kbase + (c + 1) * 32 < p.S;
             if (c & 1) {
               if (next_live) tmem_ld32(tS + (c + 1) * 32, va);
-              if (live) softmax_chunk<POLY, PACK>(vb, h, sl2e, mb, b0, b1, sum, ragged, kbase + c * 32, p.S);
+              if (live) softmax_chunk(vb, h, sl2e, mb, b0, b1, sum, ragged, kbase + c * 32, p.S);
             } else {
               if (next_live) tmem_ld32(tS + (c + 1) * 32, vb);
-              if (live) softmax_chunk<POLY, PACK>(va, h, sl2e, mb, b0, b1, sum, ragged, kbase + c * 32, p.S);
+              if (live) softmax_chunk(va, h, sl2e, mb, b0, b1, sum, ragged, kbase + c * 32, p.S);
             }
             if (!live) {
 #pragma unroll
@@ -412,11 +400,11 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
               tc_fence_after();
               pv_pending = false;
             }
-            if (dbg && x == 0 && dn < 32) p.dbg[3072 + dn * 16 + c * 3 + 2] = clock64();
             tmem_st16(tP + c * 16, h);
           }
-          bmax = fmaxf(b0, b1);
-          // f16 P overflows beyond 2^16: redo the whole block with the exact max (all lanes: the TMEM ops are warp-collective)
+          bmax = exchange_max(fmaxf(b0, b1));   // block max of the whole row: both threads of a row take identical decisions
+          // f16 P overflows beyond 2^16: redo the whole block with the exact max (all lanes: the TMEM ops are warp-collective;
+          // the partner warp holds the same rows, hence the same vote)
           const bool over = (bmax - ref) * sl2e > 15.0f;
           redo = __any_sync(0xffffffffu, over);
           if (over) ref = bmax;
@@ -430,7 +418,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
             const float alpha = moved ? ex2_approx((m_prev - ref) * sl2e) : 1.0f;
             l *= alpha;
 #pragma unroll 1
-            for (int c = 0; c < 64; c += 32) {
+            for (int c = 0; c < OCOLS; c += 32) {
               uint32_t o[32];
               tmem_ld32(tO + c, o);
               tmem_ld_wait();
@@ -440,7 +428,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
             }
           }
         }
-        l += sum;
+        l += sum;                                        // partial sum over this thread's columns
         m_prev = ref;
         m = ((bmax - ref) * sl2e > 8.0f) ? bmax : ref;   // reference for the next block
         tmem_st_wait();
@@ -450,14 +438,21 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         ++dn;
       }
       // ---- write-back: O / l -> f16 (the next item's Q K^T and first exp phase overlap this)
+      {
+        float* slot = xchg + (((xk & 1) * 2 + x) * 2) * 128;
+        slot[hf * 128 + r] = l;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + x * 4 + q) : "memory");
+        l += slot[(hf ^ 1) * 128 + r];
+        ++xk;
+      }
       mbar_wait(&o_full[x], o_ph);
       o_ph ^= 1u;
       tc_fence_after();
       const int t = qt * 128 + x * 128 + r;
       const float inv = 1.0f / l;
-      __half* o = p.out + ((size_t)b * p.T + t) * p.ldo + head * 64;
+      __half* o = p.out + ((size_t)b * p.T + t) * p.ldo + head * 64 + hf * OCOLS;
 #pragma unroll 1
-      for (int c = 0; c < 64; c += 32) {
+      for (int c = 0; c < OCOLS; c += 32) {
         uint32_t v[32];
         tmem_ld32(tO + c, v);
         tmem_ld_wait();
@@ -489,22 +484,6 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
 // is a per-device function attribute).
 struct AttnDev { bool attr = false; int num_sms = 0; };
 static AttnDev g_attn_dev[64];
-static int g_attn_variant = -1;   // -1: default; sdxl_dbg_attention_variant sets POLY + 4 * PACK
-void attention_set_variant(int v) { g_attn_variant = v; }
-
-typedef void (*AttnKernel)(const AttnParams);
-static AttnKernel attn_kernel_for(int v) {
-  switch (v) {
-    case 0: return attention_kernel<0, 0>;
-    case 1: return attention_kernel<1, 0>;
-    case 2: return attention_kernel<2, 0>;
-    case 4: return attention_kernel<0, 1>;
-    case 5: return attention_kernel<1, 1>;
-    case 6: return attention_kernel<2, 1>;
-    default: return nullptr;
-  }
-}
-
 int attention_launch(cudaStream_t st, const AttnParams& p) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
@@ -512,22 +491,16 @@ int attention_launch(cudaStream_t st, const AttnParams& p) {
   if (dev < 0 || dev >= 64) return 2001;
   AttnDev& D = g_attn_dev[dev];
   if (!D.attr) {
-    for (int v = 0; v < 8; ++v)
-      if (attn_kernel_for(v)) {
-        e = cudaFuncSetAttribute(attn_kernel_for(v), cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
-        if (e != cudaSuccess) return (int)e;
-      }
+    e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    if (e != cudaSuccess) return (int)e;
     cudaDeviceGetAttribute(&D.num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (D.num_sms <= 0) D.num_sms = 148;
     D.attr = true;
   }
-  static const int env_variant = getenv("SDXL_B200_ATTN_VARIANT") ? atoi(getenv("SDXL_B200_ATTN_VARIANT")) : 4;
-  AttnKernel k = attn_kernel_for(g_attn_variant >= 0 ? g_attn_variant : env_variant);
-  if (!k) k = attn_kernel_for(4);
   const long tiles = (long)p.B * p.n_head * ((p.T + 127) / 128);
   const long want = (tiles + 1) / 2;  // one two-slot item per CTA when the machine is not full
   dim3 grid((unsigned)(want < D.num_sms ? (want > 0 ? want : 1) : D.num_sms));
-  return launch_kernel(k, grid, dim3(kAttnThreads), (size_t)kAttnSmem, st, true, p);
+  return launch_kernel(attention_kernel, grid, dim3(kAttnThreads), (size_t)kAttnSmem, st, true, p);
 }
 
 }  // namespace sdxl

@@ -103,6 +103,7 @@ struct sdxl_unet {
   STrans mid_st;
   Norm norm_out;
   Conv conv_out;
+  __half* conv_out_w2 = nullptr;   // [O, 2*Ktot] = [W | W]: head conv on the hi/lo-split activation
   std::vector<double> alphas;  // host copy (f16-stored values widened)
   int n_tblocks = 0;
   // conditioning state
@@ -302,6 +303,17 @@ static int build_model(sdxl_unet* u, const PackView& pv, Arena& A) {
   u->norm_out = L.norm("norm_out", mc);
   u->conv_out = L.conv("conv_out", mc, g.out_channels, 3);
   if (L.err) return L.err;
+  // The head conv is the one GEMM whose operand-rounding error reaches eps undamped (every other layer's is averaged by what
+  // follows), so its activation operand is split hi + lo (two f16 tensors, ~22 bits): same weights twice along K.
+  {
+    const Conv& cv = u->conv_out;
+    u->conv_out_w2 = A.get<__half>((size_t)cv.O * 2 * cv.Ktot);
+    if (!u->conv_out_w2) return fail(c, 4005, "weight arena exhausted");
+    if (!A.measure)
+      for (int h2 = 0; h2 < 2; ++h2)
+        CU(c, cudaMemcpy2DAsync(u->conv_out_w2 + (size_t)h2 * cv.Ktot, (size_t)2 * cv.Ktot * sizeof(__half), cv.w, (size_t)cv.Ktot * sizeof(__half),
+                                (size_t)cv.Ktot * sizeof(__half), (size_t)cv.O, cudaMemcpyDeviceToDevice, c->stream));
+  }
 
   // concatenated lin_embed matrix (one GEMV per forward for all ResBlocks); bias += conv_in bias
   {
@@ -651,12 +663,14 @@ static int build_plan_ops(sdxl_unet* u, Plan* P, Arena* A) {
   if (B.err) return B.err;
   // --- head: GN -> SiLU -> conv 3x3 (unet/mod.rs:488-490)
   B.gn(x, Cx, nullptr, 0, H * W, u->norm_out, 1, s_gn1, nullptr);
+  if (!B.err && !P->ops.empty()) P->ops.back().gn.y_lo = s_raw;   // rounding residue of the normalised activation (hi/lo split)
   {
-    ActView a{s_gn1, Bf, H, W, Cx};
+    ActView a{s_gn1, Bf, H, W, Cx}, alo{s_raw, Bf, H, W, Cx};
     std::vector<IgemmSeg> segs;
-    for (int kh = 0; kh < 3; ++kh)
-      for (int kw = 0; kw < 3; ++kw) segs.push_back({0, (int16_t)(kw - 1), (int16_t)(kh - 1), 0, u->conv_out.Ipad / 64});
-    B.igemm(a, nullptr, segs, u->conv_out.w, u->conv_out.O, u->conv_out.Ktot, H, W, Bf, IGEMM_LINEAR, 0, P->eps, 1, P->eps_ld,
+    for (int part = 0; part < 2; ++part)   // K = [9 taps on hi | 9 taps on lo], weights [W | W]
+      for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw) segs.push_back({(int16_t)part, (int16_t)(kw - 1), (int16_t)(kh - 1), 0, u->conv_out.Ipad / 64});
+    B.igemm(a, &alo, segs, u->conv_out_w2, u->conv_out.O, 2 * u->conv_out.Ktot, H, W, Bf, IGEMM_LINEAR, 0, P->eps, 1, P->eps_ld,
             u->conv_out.b, 0, nullptr, 0);
     B.add_flops(2.0 * Bf * H * W * 9.0 * Cx * u->conv_out.O);
   }
@@ -1155,12 +1169,8 @@ extern "C" int sdxl_op_timestep_embedding(sdxl_ctx* c, const int32_t* t_host, in
   return 0;
 }
 
-// Diagnostics: selects the attention kernel variant (fraction of exponentials on the FMA pipe: 0 none, 1 a quarter, 2 half;
-// -1 restores the default). Process-wide; used by tools/attn_bench.py and the parity tests to cover every variant.
-extern "C" void sdxl_dbg_attention_variant(int poly) { attention_set_variant(poly); }
-
 // Diagnostics: clock64 stamps of CTA 0 of one attention launch on synthetic data (tools/attn_timeline.py).
-// stamps_host[4][1024]: [3][dn < 32][16] = slot A per chunk {before ld wait, after ld wait, after exp} x 4; [0..2][256][4]: role 0/1 = softmax slot A/B (one warp's lane 0): {S ready, exp phase done, P handed over, item written
+// stamps_host[3][256][4]: role 0/1 = softmax slot A/B (one warp's lane 0): {S ready, exp phase done, P handed over, item written
 // back}; role 2 = MMA issuer: {P_A ready, P V_A + Q K_A issued, P_B ready, P V_B + Q K_B issued}; per key block, in clocks.
 extern "C" int sdxl_dbg_attention_timeline(sdxl_ctx* c, int B, int T, int S, int n_head, long long* stamps_host) {
   if (!c || !stamps_host) return -1;
@@ -1171,12 +1181,12 @@ extern "C" int sdxl_dbg_attention_timeline(sdxl_ctx* c, int B, int T, int S, int
   __half* k = (__half*)Tm.get((size_t)B * S * C * 2);
   __half* v = (__half*)Tm.get((size_t)B * S * C * 2);
   __half* o = (__half*)Tm.get((size_t)B * T * C * 2);
-  long long* dbg = (long long*)Tm.get(4 * 1024 * 8);
+  long long* dbg = (long long*)Tm.get(3 * 1024 * 8);
   if (!q || !k || !v || !o || !dbg) return fail(c, 5400, "temporary allocation failed");
   CU(c, cudaMemsetAsync(q, 0, (size_t)B * T * C * 2, c->stream));
   CU(c, cudaMemsetAsync(k, 0, (size_t)B * S * C * 2, c->stream));
   CU(c, cudaMemsetAsync(v, 0, (size_t)B * S * C * 2, c->stream));
-  CU(c, cudaMemsetAsync(dbg, 0, 4 * 1024 * 8, c->stream));
+  CU(c, cudaMemsetAsync(dbg, 0, 3 * 1024 * 8, c->stream));
   AttnParams p{};
   p.T = T; p.S = S; p.n_head = n_head; p.B = B;
   p.out = o; p.ldo = C;
@@ -1188,7 +1198,7 @@ extern "C" int sdxl_dbg_attention_timeline(sdxl_ctx* c, int B, int T, int S, int
   for (int i = 0; i < 3; ++i) KL(c, attention_launch(c->stream, p));
   p.dbg = dbg;
   KL(c, attention_launch(c->stream, p));
-  CU(c, cudaMemcpyAsync(stamps_host, dbg, 4 * 1024 * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(stamps_host, dbg, 3 * 1024 * 8, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
   return 0;
 }

@@ -59,7 +59,7 @@ inline int launch_kernel_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block
 // Implicit GEMM on tcgen05 (igemm.cu): out[pixel, n] = epilogue( sum_seg sum_c A_seg[pixel+tap, c] *
 // Wt[n, k(seg,c)] ). Linear layers are the 1-segment / 1x1 case of the same kernel.
 // ------------------------------------------------------------------------------------------------
-constexpr int IGEMM_MAX_SEG = 12;
+constexpr int IGEMM_MAX_SEG = 20;
 struct IgemmSeg {
   int16_t map;   // 0 -> tmA0, 1 -> tmA1
   int16_t dw, dh;  // tap offset added to the tile's (w0,h0)
@@ -145,8 +145,6 @@ struct AttnParams {
 };
 int make_tmap_rows(CUtensorMap* tm, const __half* base, int rows_per_batch, int nbatch, int cols, int pitch);
 int attention_launch(cudaStream_t st, const AttnParams& p);
-// diagnostics: kernel variant = POLY + 4 * PACK (attention.cu); -1: default / SDXL_B200_ATTN_VARIANT
-void attention_set_variant(int v);
 
 // ------------------------------------------------------------------------------------------------
 // Norms (norm.cu)
@@ -164,6 +162,7 @@ struct GnParams {
   __half* raw;                // nullable: un-normalised f16 copy of cat([x1,x2]) (skip-conv operand)
   float* partial;             // scratch of gn_scratch_floats(B, n_group) floats, initialised once with gn_scratch_init
   int nchunk;                 // filled by gn_launch
+  __half* y_lo;               // nullable: f16(t - float(y)), the rounding residue of y (hi/lo split operand of the UNet's last conv)
 };
 size_t gn_scratch_floats(int B, int n_group);
 // zeroes the arrival counters of a freshly allocated scratch (once; the kernels leave them at zero)

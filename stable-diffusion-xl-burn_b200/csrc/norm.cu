@@ -21,6 +21,22 @@ int gn_scratch_init(cudaStream_t st, float* scratch, int B, int n_group) {
   return (int)cudaMemsetAsync(gn_counters(scratch, B, n_group), 0, ((size_t)B + 16) * sizeof(unsigned), st);
 }
 
+// Pivot of a (sample, group): the mean of four of its elements (first / middle channel at the first / middle pixel). Sums are
+// taken of (x - pivot), so that var = E[(x-K)^2] - E[x-K]^2 has no cancellation when |mean| >> sigma (the reference centres
+// first, groupnorm/mod.rs:75-82; real activations have groups with |mean| / sigma in the hundreds). Same value in every CTA.
+__device__ __forceinline__ float gn_pivot(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2, int b, int HW,
+                                          int c0, int cpg) {
+  float k = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int c = c0 + i * (cpg >> 1);
+    const float* src = c < C1 ? x1 + (size_t)b * HW * C1 + c : x2 + (size_t)b * HW * C2 + (c - C1);
+    const int Cs = c < C1 ? C1 : C2;
+    k += __ldg(src) + __ldg(src + (size_t)(HW >> 1) * Cs);
+  }
+  return 0.25f * k;
+}
+
 // ---- stats: grid (nchunk, B); block = V*R threads, V = C/4 float4 columns, R pixel rows in flight.
 // The last CTA of a sample to finish (arrival counter; control only, the arithmetic order is fixed) turns the chunk partials
 // into the sample's (mean, rstd) per group, so the apply kernel does not repeat that in every CTA.
@@ -43,6 +59,18 @@ __global__ void gn_stats_kernel(const float* __restrict__ x1, int C1, const floa
   int cc, Cs;
   if (c < C1) { src = x1; cc = c; Cs = C1; } else { src = x2; cc = c - C1; Cs = C2; }
   src += (size_t)b * HW * Cs + cc;
+  const int cpg = C / n_group;
+  // per-channel pivot = pivot of the channel's group (a float4 may straddle two groups)
+  float4 K;
+  {
+    const int g0 = c / cpg, g3 = (c + 3) / cpg;
+    const float k0 = gn_pivot(x1, C1, x2, C2, b, HW, g0 * cpg, cpg);
+    const float k3 = g3 == g0 ? k0 : gn_pivot(x1, C1, x2, C2, b, HW, g3 * cpg, cpg);
+    K.x = k0;
+    K.y = (c + 1) / cpg == g0 ? k0 : k3;
+    K.z = (c + 2) / cpg == g0 ? k0 : k3;
+    K.w = k3;
+  }
   float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
   int p = p0 + rr;
   for (; p + 7 * R < p1; p += 8 * R) {  // eight independent 128-bit loads in flight per thread
@@ -51,20 +79,21 @@ __global__ void gn_stats_kernel(const float* __restrict__ x1, int C1, const floa
     for (int u = 0; u < 8; ++u) a[u] = *reinterpret_cast<const float4*>(src + (size_t)(p + u * R) * Cs);
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      s.x += a[u].x; s.y += a[u].y; s.z += a[u].z; s.w += a[u].w;
-      q.x = fmaf(a[u].x, a[u].x, q.x); q.y = fmaf(a[u].y, a[u].y, q.y);
-      q.z = fmaf(a[u].z, a[u].z, q.z); q.w = fmaf(a[u].w, a[u].w, q.w);
+      const float dx = a[u].x - K.x, dy = a[u].y - K.y, dz = a[u].z - K.z, dw = a[u].w - K.w;
+      s.x += dx; s.y += dy; s.z += dz; s.w += dw;
+      q.x = fmaf(dx, dx, q.x); q.y = fmaf(dy, dy, q.y);
+      q.z = fmaf(dz, dz, q.z); q.w = fmaf(dw, dw, q.w);
     }
   }
   for (; p < p1; p += R) {
     const float4 a = *reinterpret_cast<const float4*>(src + (size_t)p * Cs);
-    s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
-    q.x = fmaf(a.x, a.x, q.x); q.y = fmaf(a.y, a.y, q.y); q.z = fmaf(a.z, a.z, q.z); q.w = fmaf(a.w, a.w, q.w);
+    const float dx = a.x - K.x, dy = a.y - K.y, dz = a.z - K.z, dw = a.w - K.w;
+    s.x += dx; s.y += dy; s.z += dz; s.w += dw;
+    q.x = fmaf(dx, dx, q.x); q.y = fmaf(dy, dy, q.y); q.z = fmaf(dz, dz, q.z); q.w = fmaf(dw, dw, q.w);
   }
   float* row = sm + ((size_t)rr * C + c) * 2;
   row[0] = s.x; row[1] = q.x; row[2] = s.y; row[3] = q.y; row[4] = s.z; row[5] = q.z; row[6] = s.w; row[7] = q.w;
   __syncthreads();
-  const int cpg = C / n_group;
   if (threadIdx.x < n_group) {
     const int g = threadIdx.x;
     float S = 0.f, Q = 0.f;
@@ -106,10 +135,10 @@ __global__ void gn_stats_kernel(const float* __restrict__ x1, int C1, const floa
     }
     if (sub == 0) {
       const double n = (double)cpg * HW;
-      const double m = S / n;
+      const double m = S / n;               // mean of (x - pivot): O(sigma), so the subtraction below does not cancel
       double var = Q / n - m * m;
       if (var < 0.0) var = 0.0;
-      final_stats[((size_t)b * n_group + g) * 2] = (float)m;
+      final_stats[((size_t)b * n_group + g) * 2] = (float)((double)gn_pivot(x1, C1, x2, C2, b, HW, g * cpg, cpg) + m);
       final_stats[((size_t)b * n_group + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
     }
   }
@@ -120,7 +149,8 @@ __global__ void gn_stats_kernel(const float* __restrict__ x1, int C1, const floa
 // pixel rows, no index divisions in the loop
 __global__ void gn_apply_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2, int HW,
                                 int n_group, const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
-                                const float* __restrict__ final_stats, int R, __half* __restrict__ y, __half* __restrict__ raw) {
+                                const float* __restrict__ final_stats, int R, __half* __restrict__ y, __half* __restrict__ raw,
+                                __half* __restrict__ y_lo) {
   griddep_wait();
   griddep_launch_dependents();
   const int C = C1 + C2;
@@ -130,13 +160,14 @@ __global__ void gn_apply_kernel(const float* __restrict__ x1, int C1, const floa
   const int b = blockIdx.y;
   const int cpg = C / n_group;
   const int c = v * 8;
-  float sc[8], sh[8];
+  float sc[8], sh[8], mu[8];   // y = (x - mean) * (rstd * gamma) + beta: centre first (exact in f32 when x is near the mean)
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int g = (c + i) / cpg;
     const float mean = final_stats[((size_t)b * n_group + g) * 2], rstd = final_stats[((size_t)b * n_group + g) * 2 + 1];
     sc[i] = rstd * gamma[c + i];
-    sh[i] = beta[c + i] - mean * sc[i];
+    sh[i] = beta[c + i];
+    mu[i] = mean;
   }
   const float* src;
   int cc, Cs;
@@ -144,6 +175,7 @@ __global__ void gn_apply_kernel(const float* __restrict__ x1, int C1, const floa
   src += (size_t)b * HW * Cs + cc;
   __half* yo = y + (size_t)b * HW * C + c;
   __half* ro = raw ? raw + (size_t)b * HW * C + c : nullptr;
+  __half* lo = y_lo ? y_lo + (size_t)b * HW * C + c : nullptr;
   const int step = gridDim.x * R;
   auto emit = [&](int p, const float4& a0, const float4& a1) {
     float f[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
@@ -158,7 +190,7 @@ __global__ void gn_apply_kernel(const float* __restrict__ x1, int C1, const floa
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      float t = fmaf(f[i], sc[i], sh[i]);
+      float t = fmaf(f[i] - mu[i], sc[i], sh[i]);
       if (silu) t = silu_f(t);
       f[i] = t;
     }
@@ -166,8 +198,21 @@ __global__ void gn_apply_kernel(const float* __restrict__ x1, int C1, const floa
     for (int i = 0; i < 4; ++i) {
       __half2 t = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
       h[i] = *reinterpret_cast<uint32_t*>(&t);
+      if (lo) {   // what the f16 rounding dropped (exact in f32), itself rounded to f16: y + y_lo carries ~22 bits of t
+        const float2 back = __half22float2(t);
+        f[2 * i] -= back.x;
+        f[2 * i + 1] -= back.y;
+      }
     }
     *reinterpret_cast<uint4*>(yo + (size_t)p * C) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (lo) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        __half2 t = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+        h[i] = *reinterpret_cast<uint32_t*>(&t);
+      }
+      *reinterpret_cast<uint4*>(lo + (size_t)p * C) = make_uint4(h[0], h[1], h[2], h[3]);
+    }
   };
   int p = blockIdx.x * R + rr;
   for (; p + 3 * step < HW; p += 4 * step) {  // four rows (eight 16-byte loads) in flight per thread
@@ -221,7 +266,7 @@ int gn_launch(cudaStream_t st, GnParams& p) {
   if (ctas > cap) ctas = cap;
   if (ctas < 1) ctas = 1;
   return launch_kernel(gn_apply_kernel, dim3(ctas, p.B), dim3(V8 * R2), (size_t)0, st, true, p.x1, p.C1, p.x2, p.C2, p.HW,
-                       p.n_group, p.gamma, p.beta, p.silu, (const float*)fin, R2, p.y, p.raw);
+                       p.n_group, p.gamma, p.beta, p.silu, (const float*)fin, R2, p.y, p.raw, p.y_lo);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -120,10 +120,7 @@ def test_layer_norm(ctx, rows, C):
 
 @pytest.mark.parametrize("B,T,S,nh", [(1, 256, 256, 2), (2, 1024, 1024, 4), (2, 1024, 77, 20), (1, 4096, 77, 10),
                                       (1, 64, 64, 1), (2, 16, 3, 4), (1, 200, 333, 2), (1, 4096, 4096, 2)])
-@pytest.mark.parametrize("poly", [0, 2, 4, 5])
-def test_qkv_attention(ctx, B, T, S, nh, poly):
-    """kernel variants POLY + 4 * PACK (csrc/attention.cu): MUFU / FMA-pipe exponentials, F2FP / integer truncating pack of P"""
-    ctx.lib.sdxl_dbg_attention_variant(poly)
+def test_qkv_attention(ctx, B, T, S, nh):
     g = torch.Generator().manual_seed(T + S + nh)
     C = nh * 64
     q = h16(torch.randn(B, T, C, generator=g))
@@ -131,20 +128,17 @@ def test_qkv_attention(ctx, B, T, S, nh, poly):
     v = h16(torch.randn(B, S, C, generator=g))
     ref = O.qkv_attention(q.float(), k.float(), v.float(), None, nh)
     out = ctx.qkv_attention(q, k, v, None, nh)
-    ctx.lib.sdxl_dbg_attention_variant(-1)
     # P is rounded to f16 before the PV contraction and the output is f16: ~2^-11 relative each
     e = rel_err(out, ref)
-    print(f"attention B={B} T={T} S={S} heads={nh} poly={poly}: rel err {e:.3e}")
+    print(f"attention B={B} T={T} S={S} heads={nh}: rel err {e:.3e}")
     assert e < 1.0e-3
     assert torch.isfinite(out).all()
 
 
-@pytest.mark.parametrize("poly", [0, 4, 6])
 @pytest.mark.parametrize("scale", [1.5, 3.0, 6.0])
-def test_qkv_attention_large_dynamic_range(ctx, scale, poly):
+def test_qkv_attention_large_dynamic_range(ctx, scale):
     """Scores whose row maximum jumps between key blocks — by a little (lazy reference kept), by more than 2^8 (the row's
     O accumulator is rescaled in TMEM) and by far more than 2^15 (overflow fallback: the block is re-run with its exact max)."""
-    ctx.lib.sdxl_dbg_attention_variant(poly)
     g = torch.Generator().manual_seed(int(scale * 10))
     B, T, S, nh = 1, 256, 640, 2
     q = h16(torch.randn(B, T, nh * 64, generator=g) * scale)
@@ -153,10 +147,9 @@ def test_qkv_attention_large_dynamic_range(ctx, scale, poly):
     v = h16(torch.randn(B, S, nh * 64, generator=g))
     ref = O.qkv_attention(q.float(), k.float(), v.float(), None, nh)
     out = ctx.qkv_attention(q, k, v, None, nh)
-    ctx.lib.sdxl_dbg_attention_variant(-1)
     assert torch.isfinite(out).all()
     e = rel_err(out, ref)
-    print(f"attention dynamic range scale {scale} poly {poly}: rel err {e:.3e}")
+    print(f"attention dynamic range scale {scale}: rel err {e:.3e}")
     assert e < 2e-3
 
 

@@ -1,10 +1,9 @@
 #!/usr/bin/env python
-"""Attention kernel microbenchmark on the UNet's own shapes (SDXL base 1024^2, CFG-batched B=2), per kernel variant.
+"""Attention kernel microbenchmark on the UNet's own shapes (SDXL base 1024^2, CFG-batched B=2).
 
     python tools/attn_bench.py [out.json]
 
-For each (T, S, heads) of the step and each variant (fraction of exponentials on the FMA pipe: 0, 1/4, 1/2) it reports
-the mean CUDA-event time of `sdxl_qkv_attention` over 20 launches (inputs rotate through 4 buffers; outputs are checked
+For each (T, S, heads) of the step it reports the mean CUDA-event time of `sdxl_qkv_attention` over 20 launches (inputs rotate through 4 buffers; outputs are checked
 against a float32 torch reference on the same device), the algorithmic TFLOP/s (4*B*T*S*C) and the fraction of the
 measured tensor peak. `per_step_ms` weights the shapes by how often one sampler step launches them (60/10/60/10).
 """
@@ -19,7 +18,6 @@ for p in (ROOT, os.path.join(ROOT, "stable-diffusion-xl-burn_b200")):
 import torch  # noqa: E402
 import sdxl_b200  # noqa: E402
 
-VARIANTS = (0, 4, 5, 6)   # POLY + 4 * PACK (csrc/attention.cu)
 SHAPES = [  # (T, S, heads, launches per sampler step)
     (1024, 1024, 20, 60), (4096, 4096, 10, 10), (1024, 77, 20, 60), (4096, 77, 10, 10)]
 
@@ -29,8 +27,7 @@ def main():
     lib = ctx.lib
     res = {"variants": {}}
     B = 2
-    for poly in VARIANTS:
-        lib.sdxl_dbg_attention_variant(poly)
+    for poly in (0,):
         rows, per_step = [], 0.0
         for T, S, nh, count in SHAPES:
             C = nh * 64
@@ -61,9 +58,8 @@ def main():
             fl = 4.0 * B * T * S * C
             rows.append({"T": T, "S": S, "heads": nh, "us": round(us, 2), "tflops": round(fl / us * 1e-6, 1), "rel_err_vs_f32": err})
             per_step += us * count * 1e-3
-        res["variants"][f"variant{poly}"] = {"shapes": rows, "per_step_ms": round(per_step, 3)}
-        print(f"variant {poly}: per-step attention {per_step:.3f} ms :: " + " | ".join(f"T{r['T']} S{r['S']}: {r['us']} us ({r['tflops']} TF/s, err {r['rel_err_vs_f32']:.1e})" for r in rows), flush=True)
-    lib.sdxl_dbg_attention_variant(-1)
+        res = {"shapes": rows, "per_step_ms": round(per_step, 3)}
+        print(f"per-step attention {per_step:.3f} ms :: " + " | ".join(f"T{r['T']} S{r['S']}: {r['us']} us ({r['tflops']} TF/s, err {r['rel_err_vs_f32']:.1e})" for r in rows), flush=True)
     if len(sys.argv) > 1:
         with open(sys.argv[1], "w") as fh:
             json.dump(res, fh, indent=1)

@@ -1,14 +1,13 @@
 #!/usr/bin/env python
-"""Per-launch timing of back-to-back attention launches (looks for rare long stalls): python tools/attn_stall.py variant T S heads n"""
+"""Per-launch timing of back-to-back attention launches (looks for rare long stalls): python tools/attn_stall.py T S heads n"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "stable-diffusion-xl-burn_b200")):
     sys.path.insert(0, p)
 import torch
 import sdxl_b200
-v, T, S, nh, n = (int(a) for a in sys.argv[1:6])
+T, S, nh, n = (int(a) for a in sys.argv[1:5])
 ctx = sdxl_b200.Context(0)
-ctx.lib.sdxl_dbg_attention_variant(v)
 B, C = 2, nh * 64
 g = torch.Generator(device="cuda").manual_seed(1)
 q, k, vv = (torch.randn(B, L, C, device="cuda", generator=g).half() for L in (T, S, S))
@@ -21,4 +20,4 @@ for i in range(n):
     ev[i + 1].record(ctx.stream)
 ctx.synchronize()
 ts = [ev[i].elapsed_time(ev[i + 1]) * 1e3 for i in range(n)]
-print(f"variant {v} T{T} S{S}: min {min(ts):.1f} us median {sorted(ts)[n//2]:.1f} max {max(ts):.1f}; >3x median: {[ (i, round(t)) for i, t in enumerate(ts) if t > 3 * sorted(ts)[n//2]]}")
+print(f"T{T} S{S}: min {min(ts):.1f} us median {sorted(ts)[n//2]:.1f} max {max(ts):.1f}; >3x median: {[ (i, round(t)) for i, t in enumerate(ts) if t > 3 * sorted(ts)[n//2]]}")

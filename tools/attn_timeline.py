@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """In-kernel timeline of the attention kernel (CTA 0): per key block, when S became ready, when the exp phase ended, when P was
 handed to the MMA warp, and when the MMA warp saw P / finished issuing. Clocks relative to the first stamp.
-    python tools/attn_timeline.py [T S heads [poly]]"""
+    python tools/attn_timeline.py [T S heads]"""
 import ctypes as C
 import os
 import sys
@@ -12,14 +12,12 @@ for p in (ROOT, os.path.join(ROOT, "stable-diffusion-xl-burn_b200")):
 import sdxl_b200  # noqa: E402
 
 T, S, nh = (int(a) for a in sys.argv[1:4]) if len(sys.argv) >= 4 else (1024, 1024, 20)
-poly = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 ctx = sdxl_b200.Context(0)
-ctx.lib.sdxl_dbg_attention_variant(poly)
-buf = (C.c_longlong * (4 * 1024))()
+buf = (C.c_longlong * (3 * 1024))()
 ctx.check(ctx.lib.sdxl_dbg_attention_timeline(ctx.h, 2, T, S, nh, buf), "timeline")
 st = [[[buf[r * 1024 + j * 4 + k] for k in range(4)] for j in range(256)] for r in range(3)]
 t0 = min(v for r in st for j in r for v in j if v > 0)
-print(f"T={T} S={S} heads={nh} poly={poly}; clocks since the first stamp")
+print(f"T={T} S={S} heads={nh}; clocks since the first stamp")
 print(" blk |   A: S ready  exp done  P handed  (item out) |   B: S ready  exp done  P handed  (item out) | MMA: P_A seen  A issued  P_B seen  B issued")
 for j in range(256):
     if not any(st[r][j][0] for r in range(3)):
@@ -27,9 +25,3 @@ for j in range(256):
     f = lambda v: f"{v - t0:9d}" if v > 0 else "        -"  # noqa: E731
     print(f"{j:4d} | " + " ".join(f(st[0][j][k]) for k in range(4)) + " | " + " ".join(f(st[1][j][k]) for k in range(4)) + " | " + " ".join(f(st[2][j][k]) for k in range(4)))
 
-print("slot A, per 32-column chunk: wait for the TMEM load / exponentials+pack (clocks)")
-for j in range(12):
-    row = [buf[3072 + j * 16 + k] for k in range(12)]
-    if not row[0]:
-        break
-    print(f"{j:4d} | " + " | ".join(f"ldwait {row[c*3+1]-row[c*3]:5d} exp {row[c*3+2]-row[c*3+1]:5d}" for c in range(4)) + f" | start {row[0]-t0:8d} end {row[11]-t0:8d}")
