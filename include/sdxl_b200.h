@@ -95,6 +95,14 @@ SDXL_API uint64_t sdxl_ctx_launch_count(const sdxl_ctx* ctx);
  * (pack_on_device); the library keeps its own re-laid-out copy, the caller may free the pack. */
 SDXL_API int sdxl_unet_load(sdxl_ctx* ctx, const sdxl_unet_cfg* cfg, const void* pack, size_t bytes,
                    int pack_on_device, sdxl_unet** out);
+/* Multi-GPU load: prompt-sharded replicas, one process (or thread) per GPU. EVERY rank of `nccl_comm`
+ * (an ncclComm_t the host application created, e.g. with ncclCommInitRank) calls this with the same cfg; only `root` passes a
+ * pack (host or device), the other ranks pass pack = NULL, bytes = 0. One ncclBroadcast of the flat pack over NVLink on the
+ * ctx stream (preceded by an 8-byte broadcast of its size), then the same local re-layout as sdxl_unet_load. No collective is
+ * ever issued inside the sampling loop. libnccl.so.2 is resolved at first use (the copy already loaded in the process, else
+ * $SDXL_B200_NCCL_LIB, else the loader path); without it the call fails with an error, the rest of the library works. */
+SDXL_API int sdxl_unet_load_broadcast(sdxl_ctx* ctx, const sdxl_unet_cfg* cfg, const void* pack, size_t bytes, int pack_on_device,
+                                      void* nccl_comm, int rank, int root, sdxl_unet** out);
 SDXL_API void sdxl_unet_destroy(sdxl_unet* unet);
 /* Step-invariant part of UNet::forward, hoisted: cross-attention K/V projections of `context`
  * (unet/mod.rs:1010-1011 for attn2) and the label-embedding MLP (unet/mod.rs:464-466).
@@ -146,6 +154,9 @@ SDXL_API double sdxl_unet_alpha(const sdxl_unet* unet, int i);
  * the launch plan currently built for this UNet (0 before the first forward). */
 SDXL_API double sdxl_unet_plan_flops(const sdxl_unet* unet);
 SDXL_API int sdxl_unet_plan_num_ops(const sdxl_unet* unet);
+/* FLOPs the plan's tensor-core launches actually issue: without the K/V projections hoisted to set_conditioning, with the
+ * phase-decomposed upsample convolutions at their real cost and with channel / key padding (bench: `executed_flops`). */
+SDXL_API double sdxl_unet_plan_flops_executed(const sdxl_unet* unet);
 /* Device time of ONE execution of the current launch plan, summed per kernel kind and measured with CUDA
  * events on the ctx stream (eager launches). Kind index: 0 implicit-GEMM (tcgen05), 1 attention, 2 GroupNorm,
  * 3 LayerNorm, 4 GEMV, 5 timestep-embedding, 6 first conv, 7 upsample copy, 8 phase-split copy, 9 f32->f16 cast.

@@ -474,39 +474,6 @@ __global__ void vec_add_f32_kernel(float* __restrict__ dst, const float* __restr
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] += src[i];
 }
-// LayerNorm fold at load time (one warp per output row n of the K-major matrix W[n, k]):
-//   v[n] = sum_k beta[k] * W[n,k] (+ bias[n]);  W[n,k] <- f16(gamma[k] * W[n,k]);  u[n] = sum_k W'[n,k]
-// so that LayerNorm(x) W + b == rstd * (x W' - mean * u) + v. u is summed from the ROUNDED products: the tensor core sees
-// exactly those values, which makes the mean cancellation exact up to accumulation order.
-__global__ void ln_fold_kernel(__half* __restrict__ W, int N, int K, int Kpad, const float* __restrict__ gamma,
-                               const float* __restrict__ beta, const float* __restrict__ bias, float* __restrict__ u,
-                               float* __restrict__ v) {
-  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (n >= N) return;
-  __half* row = W + (size_t)n * Kpad;
-  float su = 0.f, sv = 0.f;
-  for (int k = lane; k < K; k += 32) {
-    const float w = __half2float(row[k]);
-    sv = fmaf(beta[k], w, sv);
-    const __half wf = __float2half_rn(gamma[k] * w);
-    row[k] = wf;
-    su += __half2float(wf);
-  }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) {
-    su += __shfl_xor_sync(0xffffffffu, su, o);
-    sv += __shfl_xor_sync(0xffffffffu, sv, o);
-  }
-  if (lane == 0) {
-    u[n] = su;
-    v[n] = sv + (bias ? bias[n] : 0.f);
-  }
-}
-int ln_fold_launch(cudaStream_t st, __half* W, int N, int K, int Kpad, const float* gamma, const float* beta, const float* bias,
-                   float* u, float* v) {
-  ln_fold_kernel<<<cdiv(N, 8), 256, 0, st>>>(W, N, K, Kpad, gamma, beta, bias, u, v);
-  return (int)cudaGetLastError();
-}
 int vec_add_f32_launch(cudaStream_t st, float* dst, const float* src, int n) {
   vec_add_f32_kernel<<<cdiv(n, 256), 256, 0, st>>>(dst, src, n);
   return (int)cudaGetLastError();

@@ -182,14 +182,6 @@ static STrans load_st(Loader& L, const std::string& path, int C, int ctx_dim, in
     if (!gbn) { L.err = fail(L.c, 4009, "GEGLU width %d not tileable", 4 * C); break; }
     b.ff1 = L.linear(bp + "/mlp/geglu/proj", C, 8 * C, true, gbn);
     b.ff2 = L.linear(bp + "/mlp/lin", 4 * C, C, true);
-    // LayerNorm fold (SDXL_B200_LN_FOLD=1; default decided by the measurements in profiles/README.md): norm1 -> qkv,
-    // norm2 -> attn2/query, norm3 -> GEGLU projection (each LayerNorm has exactly one consumer, unet/mod.rs:885-891).
-    static const bool fold = getenv("SDXL_B200_LN_FOLD") != nullptr && atoi(getenv("SDXL_B200_LN_FOLD")) != 0;
-    if (fold) {
-      L.fold_ln(b.qkv, b.n1);
-      L.fold_ln(b.q2, b.n2);
-      L.fold_ln(b.ff1, b.n3);
-    }
     s.blocks.push_back(b);
   }
   return s;
@@ -351,8 +343,73 @@ static int build_model(sdxl_unet* u, const PackView& pv, Arena& A) {
 
 extern "C" void sdxl_unet_destroy(sdxl_unet* u);
 
+static int unet_load_impl(sdxl_ctx* c, const sdxl_unet_cfg* cfg, const void* pack, size_t bytes, int pack_on_device, sdxl_unet** out);
+
 extern "C" int sdxl_unet_load(sdxl_ctx* c, const sdxl_unet_cfg* cfg, const void* pack, size_t bytes, int pack_on_device,
                               sdxl_unet** out) {
+  return unet_load_impl(c, cfg, pack, bytes, pack_on_device, out);
+}
+
+// ---- NCCL, resolved at run time (no link-time dependency: the library must load on machines without it) ----
+#include <dlfcn.h>
+namespace {
+typedef int (*PFN_ncclBroadcast)(const void*, void*, size_t, int /*ncclDataType_t*/, int, void* /*ncclComm_t*/, cudaStream_t);
+typedef const char* (*PFN_ncclGetErrorString)(int);
+struct NcclApi { PFN_ncclBroadcast bcast = nullptr; PFN_ncclGetErrorString errstr = nullptr; bool tried = false; };
+NcclApi& nccl_api() {
+  static NcclApi api;
+  if (!api.tried) {
+    api.tried = true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);   // the copy the host application (e.g. torch) already loaded
+    if (!h && getenv("SDXL_B200_NCCL_LIB")) h = dlopen(getenv("SDXL_B200_NCCL_LIB"), RTLD_NOW);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW);
+    if (h) {
+      api.bcast = (PFN_ncclBroadcast)dlsym(h, "ncclBroadcast");
+      api.errstr = (PFN_ncclGetErrorString)dlsym(h, "ncclGetErrorString");
+    }
+  }
+  return api;
+}
+}  // namespace
+
+extern "C" int sdxl_unet_load_broadcast(sdxl_ctx* c, const sdxl_unet_cfg* cfg, const void* pack, size_t bytes, int pack_on_device,
+                                        void* nccl_comm, int rank, int root, sdxl_unet** out) {
+  if (!c || !cfg || !out) return fail(c, -1, "sdxl_unet_load_broadcast: null argument");
+  *out = nullptr;
+  if (!nccl_comm) return fail(c, 4300, "sdxl_unet_load_broadcast: null NCCL communicator");
+  if (rank == root && (!pack || !bytes)) return fail(c, 4301, "sdxl_unet_load_broadcast: the root rank must pass the weight pack");
+  NcclApi& N = nccl_api();
+  if (!N.bcast) return fail(c, 4302, "sdxl_unet_load_broadcast: libnccl.so.2 not found (set SDXL_B200_NCCL_LIB)");
+  CU(c, cudaSetDevice(c->device));
+  const int ncclUint8 = 1;
+  // 1. the size, so that non-root ranks can allocate
+  unsigned long long* dsz = nullptr;
+  CU(c, cudaMalloc((void**)&dsz, 8));
+  unsigned long long hsz = rank == root ? (unsigned long long)bytes : 0ull;
+  cudaError_t e = cudaMemcpyAsync(dsz, &hsz, 8, cudaMemcpyHostToDevice, c->stream);
+  int nr = e == cudaSuccess ? N.bcast(dsz, dsz, 8, ncclUint8, root, nccl_comm, c->stream) : 0;
+  if (e == cudaSuccess && !nr) e = cudaMemcpyAsync(&hsz, dsz, 8, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess && !nr) e = cudaStreamSynchronize(c->stream);
+  cudaFree(dsz);
+  if (nr) return fail(c, 4303, "ncclBroadcast (pack size) failed: %s", N.errstr ? N.errstr(nr) : "?");
+  if (e != cudaSuccess) return fail(c, (int)e, "pack size broadcast failed: %s", cudaGetErrorString(e));
+  if (hsz < sizeof(PackHeader)) return fail(c, 4304, "broadcast pack size %llu is not a weight pack", hsz);
+  // 2. the pack itself: one flat message
+  uint8_t* dpack = nullptr;
+  CU(c, cudaMalloc((void**)&dpack, (size_t)hsz));
+  if (rank == root)
+    e = cudaMemcpyAsync(dpack, pack, (size_t)hsz, pack_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) nr = N.bcast(dpack, dpack, (size_t)hsz, ncclUint8, root, nccl_comm, c->stream);
+  if (e == cudaSuccess && !nr) e = cudaStreamSynchronize(c->stream);
+  int r = 0;
+  if (nr) r = fail(c, 4303, "ncclBroadcast (pack) failed: %s", N.errstr ? N.errstr(nr) : "?");
+  else if (e != cudaSuccess) r = fail(c, (int)e, "pack broadcast failed: %s", cudaGetErrorString(e));
+  else r = unet_load_impl(c, cfg, dpack, (size_t)hsz, 1, out);
+  cudaFree(dpack);
+  return r;
+}
+
+static int unet_load_impl(sdxl_ctx* c, const sdxl_unet_cfg* cfg, const void* pack, size_t bytes, int pack_on_device, sdxl_unet** out) {
   if (!c || !cfg || !pack || !out) return fail(c, -1, "sdxl_unet_load: null argument");
   *out = nullptr;
   if (cfg->n_head_channels != 64) return fail(c, 4200, "n_head_channels must be 64 (got %d)", cfg->n_head_channels);
@@ -442,36 +499,11 @@ struct UNetPlanBuilder : PlanBuilder {
 
   // ---- SpatialTransformer (reference unet/mod.rs:820-845, 885-891, 1005-1023) ----
   float* strans(const STrans& s, const float* x, int H, int W, __half* s_a16, float* s_tok, __half* s_qkv, __half* s_ao,
-                __half* s_q, __half* s_ff, __half* s_x16, float2* s_stats) {
+                __half* s_q, __half* s_ff) {
     const int T = H * W, M = Bf * T, C = s.C;
     float* out = buf<float>((size_t)M * C);
-    const bool fold = !s.blocks.empty() && s.blocks[0].qkv.ln_u != nullptr;
     const float sl2e = (float)(1.4426950408889634 / sqrt(64.0));
     gn(x, C, nullptr, 0, T, s.norm, 0, s_a16, nullptr);
-    if (fold) {
-      // Every LayerNorm is folded into the GEMMs around it: the residual GEMMs ("producers") emit the f16 copy of the token
-      // stream plus per-row partial statistics, the Linear after the LayerNorm ("consumer") normalises in its epilogue.
-      int slots = linear_ln_producer(s_a16, M, s.proj_in, s_tok, C, nullptr, s_x16, s_stats);
-      for (const TBlock& b : s.blocks) {
-        // x = x + attn1(norm1(x))
-        linear_ln_consumer(s_x16, M, b.qkv, IGEMM_LINEAR, s_qkv, 3 * C, s_stats, slots);
-        attn(s_qkv, 3 * C, 0, s_qkv, 3 * C, C, 2 * C, T, T, s.n_head, s_ao, C, sl2e);
-        slots = linear_ln_producer(s_ao, M, b.out1, s_tok, C, s_tok, s_x16, s_stats);
-        // x = x + attn2(norm2(x), context)   (K/V hoisted to set_conditioning)
-        linear_ln_consumer(s_x16, M, b.q2, IGEMM_LINEAR, s_q, C, s_stats, slots);
-        const __half* kvp = A->measure ? nullptr : u->kv[kv_index];
-        attn(s_q, C, 0, kvp, 2 * C, 0, C, T, u->n_ctx, s.n_head, s_ao, C, sl2e);
-        P->flops += 2.0 * Bf * u->n_ctx * (double)b.kv2.K * b.kv2.N;  // hoisted K/V projections (algorithmic work)
-        kv_index++;
-        slots = linear_ln_producer(s_ao, M, b.out2, s_tok, C, s_tok, s_x16, s_stats);
-        // x = x + mlp(norm3(x))
-        linear_ln_consumer(s_x16, M, b.ff1, IGEMM_GEGLU, s_ff, 4 * C, s_stats, slots);
-        slots = linear_ln_producer(s_ff, M, b.ff2, s_tok, C, s_tok, s_x16, s_stats);
-      }
-      // proj_out(tokens) + x_in: the last producer's f16 copy is the operand
-      linear(s_x16, M, s.proj_out, IGEMM_LINEAR, out, 1, C, x, C);
-      return out;
-    }
     linear(s_a16, M, s.proj_in, IGEMM_LINEAR, s_tok, 1, C, nullptr, 0);
     for (const TBlock& b : s.blocks) {
       // x = x + attn1(norm1(x))
@@ -517,6 +549,7 @@ struct UNetPlanBuilder : PlanBuilder {
       if (!r) p.tmV = p.tmK;
       if (r) { err = fail(c, r, "tensor map creation failed (attention)"); return; }
     }
+    op.flops_exec = 4.0 * Bf * (double)((T + 127) / 128 * 128) * (double)((S + 127) / 128 * 128) * (n_head * 64);
     P->ops.push_back(op);
     add_flops(4.0 * Bf * T * (double)S * (n_head * 64));
   }
@@ -530,6 +563,7 @@ static int build_plan_ops(sdxl_unet* u, Plan* P, Arena* A) {
   const sdxl_unet_cfg& g = u->cfg;
   UNetPlanBuilder B{{c, P, A, P->Bf}, u};
   P->ops.clear();
+  P->block_names.clear();
   P->flops = 0;
   const int Bf = P->Bf, mc = g.model_channels, ted = 4 * mc;
   const int temb_total = u->temb_all.N;
@@ -579,8 +613,6 @@ static int build_plan_ops(sdxl_unet* u, Plan* P, Arena* A) {
   __half* s_ao = B.buf<__half>(Bf * max_tokC);
   __half* s_q = B.buf<__half>(Bf * max_tokC);
   __half* s_ff = B.buf<__half>(Bf * max_tokC * 4);
-  __half* s_x16 = B.buf<__half>(Bf * max_tokC);                       // LayerNorm fold: f16 copy of the token stream
-  float2* s_stats = B.buf<float2>((size_t)PlanBuilder::kMaxLnSlots * Bf * max_tok);  // ... and per-row partial (sum, sum sq)
   if (B.err) return B.err;
 
   // --- embeddings (unet/mod.rs:458-468): emb = time_mlp(temb(t)) + label_emb; only SiLU(emb) is consumed
@@ -610,10 +642,11 @@ static int build_plan_ops(sdxl_unet* u, Plan* P, Arena* A) {
   saved.push_back({x, Cx, H, W});
   for (size_t i = 1; i < u->in_blocks.size() && !B.err; ++i) {
     const Block& b = u->in_blocks[i];
+    B.begin_block("input_blocks/" + std::to_string(i));
     if (b.type == BT_RES || b.type == BT_REST) {
       x = B.resblock(b.res, x, Cx, nullptr, 0, H, W, temb_all, temb_total, s_gn1, s_raw, s_h, s_gn2);
       Cx = b.res.Cout;
-      if (b.type == BT_REST) x = B.strans(b.st, x, H, W, s_a16, s_tok, s_qkv, s_ao, s_q, s_ff, s_x16, s_stats);
+      if (b.type == BT_REST) x = B.strans(b.st, x, H, W, s_a16, s_tok, s_qkv, s_ao, s_q, s_ff);
     } else if (b.type == BT_DOWN) {
       // 3x3 stride 2 pad 1 (unet/mod.rs:760-774) on phase-split input: tap kh -> (phase, offset)
       __half* ph = B.buf<__half>((size_t)Bf * H * W * Cx);
@@ -635,12 +668,15 @@ static int build_plan_ops(sdxl_unet* u, Plan* P, Arena* A) {
       B.add_flops(2.0 * Bf * H2 * W2 * 9.0 * Cx * b.conv.O);
       x = y; H = H2; W = W2;
     }
+    B.end_block();
     saved.push_back({x, Cx, H, W});
   }
   // --- middle
+  B.begin_block("middle_block");
   x = B.resblock(u->mid_res1, x, Cx, nullptr, 0, H, W, temb_all, temb_total, s_gn1, s_raw, s_h, s_gn2);
-  x = B.strans(u->mid_st, x, H, W, s_a16, s_tok, s_qkv, s_ao, s_q, s_ff, s_x16, s_stats);
+  x = B.strans(u->mid_st, x, H, W, s_a16, s_tok, s_qkv, s_ao, s_q, s_ff);
   x = B.resblock(u->mid_res2, x, Cx, nullptr, 0, H, W, temb_all, temb_total, s_gn1, s_raw, s_h, s_gn2);
+  B.end_block();
   // --- output blocks: cat([x, saved.pop()], channel) is never materialised (GN + skip conv read both)
   for (size_t i = 0; i < u->out_blocks.size() && !B.err; ++i) {
     const Block& b = u->out_blocks[i];
@@ -648,9 +684,10 @@ static int build_plan_ops(sdxl_unet* u, Plan* P, Arena* A) {
     Saved sk = saved.back();
     saved.pop_back();
     if (sk.H != H || sk.W != W || Cx + sk.C != b.res.Cin) return fail(c, 5005, "skip shape mismatch at output block %zu", i);
+    B.begin_block("output_blocks/" + std::to_string(i));
     x = B.resblock(b.res, x, Cx, sk.p, sk.C, H, W, temb_all, temb_total, s_gn1, s_raw, s_h, s_gn2);
     Cx = b.res.Cout;
-    if (b.type == BT_REST || b.type == BT_RESTU) x = B.strans(b.st, x, H, W, s_a16, s_tok, s_qkv, s_ao, s_q, s_ff, s_x16, s_stats);
+    if (b.type == BT_REST || b.type == BT_RESTU) x = B.strans(b.st, x, H, W, s_a16, s_tok, s_qkv, s_ao, s_q, s_ff);
     if (b.type == BT_RESTU || b.type == BT_RESU) {
       // nearest-2x then 3x3 conv (unet/mod.rs:742-751), as four 2x2 phase convolutions of the source image
       __half* x16 = B.buf<__half>((size_t)Bf * H * W * Cx);
@@ -659,8 +696,10 @@ static int build_plan_ops(sdxl_unet* u, Plan* P, Arena* A) {
       H *= 2; W *= 2;
       x = y;
     }
+    B.end_block();
   }
   if (B.err) return B.err;
+  B.begin_block("norm_out+conv_out");
   // --- head: GN -> SiLU -> conv 3x3 (unet/mod.rs:488-490)
   B.gn(x, Cx, nullptr, 0, H * W, u->norm_out, 1, s_gn1, nullptr);
   if (!B.err && !P->ops.empty()) P->ops.back().gn.y_lo = s_raw;   // rounding residue of the normalised activation (hi/lo split)
@@ -674,6 +713,7 @@ static int build_plan_ops(sdxl_unet* u, Plan* P, Arena* A) {
             u->conv_out.b, 0, nullptr, 0);
     B.add_flops(2.0 * Bf * H * W * 9.0 * Cx * u->conv_out.O);
   }
+  B.end_block();
   return B.err;
 }
 
@@ -833,6 +873,14 @@ extern "C" double sdxl_unet_alpha(const sdxl_unet* u, int i) {
 // algorithmic FLOPs of the current plan (debug / bench helper, not in the public header)
 extern "C" double sdxl_unet_plan_flops(const sdxl_unet* u) { return (u && u->plan) ? u->plan->flops : 0.0; }
 extern "C" int sdxl_unet_plan_num_ops(const sdxl_unet* u) { return (u && u->plan) ? (int)u->plan->ops.size() : 0; }
+// FLOPs the plan's tensor-core launches actually execute (see Op::flops_exec): excludes the hoisted K/V projections (not in
+// the plan), counts the phase-decomposed upsample convs at 4/9 of the algorithmic figure, includes channel / key padding.
+extern "C" double sdxl_unet_plan_flops_executed(const sdxl_unet* u) {
+  if (!u || !u->plan) return 0.0;
+  double f = 0;
+  for (const Op& o : u->plan->ops) f += o.flops_exec;
+  return f;
+}
 
 // ================================================================================================
 // sampler (Diffuser)

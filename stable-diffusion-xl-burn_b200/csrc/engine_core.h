@@ -7,6 +7,7 @@
 #include "kernels.h"
 
 #include <math.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -117,8 +118,6 @@ struct PackView {
 // ================================================================================================
 struct Lin {
   __half* w = nullptr; float* b = nullptr; int K = 0, Kpad = 0, N = 0, geglu_bn = 0;
-  // set when the preceding LayerNorm was folded into this layer at load time (IgemmParams::ln_mode 2): w holds gamma*W
-  float* ln_u = nullptr; float* ln_v = nullptr; float ln_eps = 0.f;
 };
 struct Conv {
   __half* w = nullptr; float* b = nullptr; int I = 0, O = 0, ks = 0, Ipad = 0, I2 = 0, I2pad = 0, Ktot = 0;
@@ -189,15 +188,6 @@ struct Loader {
     if (!A->measure) { int r = repack_upconv_launch(st, ptr(e), O, I, cv.wup, cv.Ipad); if (r) err = fail(c, r, "repack_upconv failed"); }
     cv.b = vec_f32(path + "/bias", O);
     return cv;
-  }
-  // Folds LayerNorm `n` into the Linear that consumes its output (elementwise.cu: ln_fold_kernel); L.b is absorbed into ln_v.
-  void fold_ln(Lin& L, const Norm& n) {
-    if (err) return;
-    L.ln_u = A->get<float>(L.N);
-    L.ln_v = A->get<float>(L.N);
-    L.ln_eps = n.eps;
-    if (!L.ln_u || !L.ln_v) { err = fail(c, 4005, "weight arena exhausted"); return; }
-    if (!A->measure) { int r = ln_fold_launch(st, L.w, L.N, L.K, L.Kpad, n.g, n.b, L.b, L.ln_u, L.ln_v); if (r) err = fail(c, r, "ln_fold failed"); }
   }
   Norm norm(const std::string& path, int C) {
     Norm n;
@@ -305,6 +295,8 @@ static const char* const kOpNames[] = {"igemm", "attention", "group_norm", "laye
 struct Op {
   OpKind kind;
   double flops = 0;  // algorithmic FLOPs of this launch (igemm / attention), 0 for HBM-bound ops
+  double flops_exec = 0;  // FLOPs the launch actually issues to the tensor cores (channel / key padding in, phase-decomposed upsample convs at their real cost)
+  int block = -1;    // index into Plan::block_names (NVTX range of the reference block this launch belongs to)
   IgemmParams ig;
   AttnParams at;
   GnParams gn;
@@ -336,6 +328,7 @@ struct Plan {
   cudaGraphExec_t gexec = nullptr;
   int runs = 0;
   double flops = 0;  // algorithmic FLOPs of one run (2*MAC over Linear/conv/attention)
+  std::vector<std::string> block_names;   // reference blocks in execution order (input_blocks/3, middle_block, ...)
   ~Plan() {
     if (gexec) cudaGraphExecDestroy(gexec);
     if (graph) cudaGraphDestroy(graph);
@@ -386,8 +379,26 @@ struct PlanBuilder {
       int r = igemm_configure(p, o, outW, outH, outB, mode, geglu_bn);
       if (r) { err = fail(c, r, "igemm configuration failed (N=%d K=%d)", N, Ktot); return; }
     }
+    {
+      double kb = 0;
+      for (int i = 0; i < p.nseg; ++i) kb += p.seg[i].nkb;
+      op.flops_exec = 2.0 * outB * outH * (double)outW * N * kb * 64.0;
+    }
     P->ops.push_back(op);
   }
+  // names the reference block the following launches belong to
+  void begin_block(const std::string& name) {
+    if (err) return;
+    P->block_names.push_back(name);
+    cur_block = (int)P->block_names.size() - 1;
+    first_op_of_block = P->ops.size();
+  }
+  void end_block() {
+    for (size_t i = first_op_of_block; i < P->ops.size(); ++i) P->ops[i].block = cur_block;
+    cur_block = -1;
+  }
+  int cur_block = -1;
+  size_t first_op_of_block = 0;
   void linear(const __half* x, int M, const Lin& L, int mode, void* out, int out_f32, int ldo, const float* res, int ldr) {
     ActView a{x, 1, 1, M, L.K};
     std::vector<IgemmSeg> segs{{0, 0, 0, 0, L.Kpad / 64}};
@@ -419,28 +430,6 @@ struct PlanBuilder {
         ig.opix_row = 4 * W; ig.opix_w = 2; ig.opix_off = pa * 2 * W + pb;
         add_flops(2.0 * Bn * H * W * 9.0 * cv.I * cv.O);
       }
-  }
-  // LayerNorm fold (kernels.h: IgemmParams::ln_mode). Producer: residual GEMM whose f32 output feeds a LayerNorm; also emits the
-  // f16 copy `x16` and per-row partial statistics. Returns the number of statistic slots (0 in the measure pass).
-  static constexpr int kMaxLnSlots = 160;  // 2 * N / 16 for N = 1280
-  int linear_ln_producer(const __half* x, int M, const Lin& L, float* out, int ldo, const float* res, __half* x16, float2* stats) {
-    // statistic slots are fixed 16-column groups of the output (independent of the tile shape: bit-exact batch invariance)
-    const int slots = L.N / 16;
-    if (L.N % 32 || slots > kMaxLnSlots) { if (!err) err = fail(c, 5006, "LayerNorm fold: width %d unsupported", L.N); return 0; }
-    linear(x, M, L, IGEMM_LINEAR, out, 1, ldo, res, ldo);
-    if (err || P->ops.empty()) return 0;
-    IgemmParams& ig = P->ops.back().ig;
-    ig.ln_mode = 1; ig.ln_x16 = x16; ig.ln_stats = stats; ig.ln_rows = M; ig.ln_slots = slots;
-    return slots;
-  }
-  // Consumer: the Linear that follows the LayerNorm (weights folded at load, Lin::ln_u / ln_v); A operand = the producer's x16.
-  void linear_ln_consumer(const __half* x16, int M, const Lin& L, int mode, void* out, int ldo, const float2* stats, int slots) {
-    linear(x16, M, L, mode, out, 0, ldo, nullptr, 0);
-    if (err || P->ops.empty()) return;
-    IgemmParams& ig = P->ops.back().ig;
-    ig.ln_mode = 2; ig.ln_stats = const_cast<float2*>(stats); ig.ln_rows = M; ig.ln_slots = slots;
-    ig.ln_u = L.ln_u; ig.ln_v = L.ln_v; ig.ln_inv_c = 1.0f / (float)L.K; ig.ln_eps = L.ln_eps;
-    ig.bias = nullptr;  // absorbed into ln_v
   }
   // 3x3 stride-1 conv (+ optional fused 1x1 skip segment on a1)
   void conv3(const ActView& a, const ActView* skip, const Conv& cv, float* out, const float* bias, int bias_bstride,
@@ -524,10 +513,17 @@ static int run_plan_ops(sdxl_ctx* c, Plan* P) {
   const bool capture = !no_graph && P->runs >= 1;  // first run eager (sets func attributes), then capture
   if (capture) CU(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
   int r = 0;
+  int open_block = -1;   // NVTX range per reference block (host side: visible in eager runs and during graph capture)
   for (auto& op : P->ops) {
+    if (op.block != open_block) {
+      if (open_block >= 0) nvtxRangePop();
+      open_block = op.block;
+      if (open_block >= 0) nvtxRangePushA(P->block_names[open_block].c_str());
+    }
     r = exec_op(c, op);
     if (r) break;
   }
+  if (open_block >= 0) nvtxRangePop();
   if (capture) {
     cudaGraph_t gph = nullptr;
     cudaError_t e = cudaStreamEndCapture(c->stream, &gph);

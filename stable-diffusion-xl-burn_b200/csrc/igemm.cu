@@ -139,7 +139,6 @@ struct EpiRow {          // per-lane description of "my" accumulator row (lane =
 struct EpiPrefetch {
   float4 res[8];
   float4 bias;            // valid when all rows of the warp share one batch (EpiRows::bb_uniform)
-  float4 u4, v4;          // LayerNorm-fold consumer: ln_u / ln_v of this lane's four columns
 };
 struct EpiRows {          // phase-2 per-lane row descriptors (constant for the whole tile)
   uint32_t off[8];        // element offset pix*ld + c4 (outputs and residual share the leading dimension)
@@ -148,57 +147,10 @@ struct EpiRows {          // phase-2 per-lane row descriptors (constant for the 
   bool bb_uniform;        // warp-uniform: every valid row has batch bb[0]-equivalent (bias row shared)
   int bb0;
 };
-// LayerNorm fold (IgemmParams::ln_mode), phase-2 mapping (lane -> rows it*4 + (lane>>3), columns (lane&7)*4 .. +3).
-// Statistic slots are fixed 16-column groups of the producer's output (slot = column / 16), whatever the tile shape, and
-// are summed in slot order by the consumer: the result does not depend on the tiling, so batch invariance stays bit-exact.
-struct LnCtx {
-  float rs[8], mr[8];     // consumer: rstd and mean*rstd of the lane's eight rows
-  uint32_t srow[8];       // producer: row * ln_slots (element offset into ln_stats)
-};
-template <int LN>
-__device__ __forceinline__ LnCtx make_ln_ctx(const IgemmParams& p, const EpiRow& me, int lane) {
-  LnCtx lc;
-  if constexpr (LN == 1) {
-    const uint32_t my = me.ok ? (uint32_t)me.pix * (uint32_t)p.ln_slots : 0u;
-#pragma unroll
-    for (int it = 0; it < 8; ++it) lc.srow[it] = __shfl_sync(0xffffffffu, my, it * 4 + (lane >> 3));
-  } else if constexpr (LN == 2) {
-    // lane = row: sum the row's slots (independent 16-byte loads, 8 in flight), then hand (rstd, mean*rstd) to the phase-2 lanes
-    float sS = 0.f, sQ = 0.f;
-    if (me.ok) {
-      const float4* sp = reinterpret_cast<const float4*>(p.ln_stats + (size_t)me.pix * p.ln_slots);
-      const int n4 = p.ln_slots >> 1;
-      for (int k0 = 0; k0 < n4; k0 += 8) {
-        float4 t[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) t[j] = (k0 + j < n4) ? __ldg(sp + k0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { sS += t[j].x; sQ += t[j].y; sS += t[j].z; sQ += t[j].w; }
-      }
-    }
-    const float mean = sS * p.ln_inv_c;
-    const float rstd = rsqrtf(fmaxf(fmaf(-mean, mean, sQ * p.ln_inv_c), 0.f) + p.ln_eps);
-    const float mrs = mean * rstd;
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      lc.rs[it] = __shfl_sync(0xffffffffu, rstd, it * 4 + (lane >> 3));
-      lc.mr[it] = __shfl_sync(0xffffffffu, mrs, it * 4 + (lane >> 3));
-    }
-  }
-  return lc;
-}
-template <int LN>
 __device__ __forceinline__ EpiPrefetch epi_prefetch(const IgemmParams& p, const EpiRows& rows, int n, int ncols, int lane) {
   EpiPrefetch f;
   const int c4 = (lane & 7) << 2;
   const bool col_ok = c4 < ncols && n + c4 < p.N;
-  if constexpr (LN == 2) {
-    // consumer: no residual, bias absorbed into ln_v
-    f.u4 = col_ok ? __ldg(reinterpret_cast<const float4*>(p.ln_u + n + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    f.v4 = col_ok ? __ldg(reinterpret_cast<const float4*>(p.ln_v + n + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    f.bias = make_float4(0.f, 0.f, 0.f, 0.f);
-    return f;
-  }
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const bool ok = ((rows.ok >> it) & 1u) && col_ok;
@@ -212,9 +164,8 @@ __device__ __forceinline__ EpiPrefetch epi_prefetch(const IgemmParams& p, const 
 }
 
 // one 32-column block (or a 16-column tail when ncols == 16) of the LINEAR epilogue; `pf` was issued earlier
-template <int LN>
 __device__ __forceinline__ void epi_linear_block(const IgemmParams& p, float* stage, uint32_t taddr, int n, int ncols,
-                                                 const EpiRows& rows, const EpiPrefetch& pf, int lane, const LnCtx& lc) {
+                                                 const EpiRows& rows, const EpiPrefetch& pf, int lane) {
   // ---- phase 1: TMEM -> registers -> smem, lane = row
   const bool dbgb = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 64 && p.dbg[9] == 0;
   if (dbgb) p.dbg[9] = globaltimer_ns();
@@ -241,42 +192,16 @@ __device__ __forceinline__ void epi_linear_block(const IgemmParams& p, float* st
   for (int it = 0; it < 8; ++it) {
     const int row = it * 4 + rr;
     const bool ok = ((rows.ok >> it) & 1u) && col_ok;
-    if (LN == 1 || ok) {   // LN == 1: every lane runs the body (warp shuffles below); stores stay guarded
+    if (ok) {
       float4 f = *reinterpret_cast<const float4*>(stage + row * kStagePitch + c4);
-      if constexpr (LN == 2) {
-        // consumer: LayerNorm applied algebraically, out = rstd * acc + (v - mean * rstd * u)
-        f.x = fmaf(lc.rs[it], f.x, fmaf(-lc.mr[it], pf.u4.x, pf.v4.x));
-        f.y = fmaf(lc.rs[it], f.y, fmaf(-lc.mr[it], pf.u4.y, pf.v4.y));
-        f.z = fmaf(lc.rs[it], f.z, fmaf(-lc.mr[it], pf.u4.z, pf.v4.z));
-        f.w = fmaf(lc.rs[it], f.w, fmaf(-lc.mr[it], pf.u4.w, pf.v4.w));
-      } else {
-        float4 b4 = pf.bias;
-        if (!rows.bb_uniform && p.bias != nullptr)  // rows of different batches in one warp tile (tiny images only)
-          b4 = __ldg(reinterpret_cast<const float4*>(p.bias + (size_t)rows.bb[it] * p.bias_bstride + n + c4));
-        f.x += b4.x + pf.res[it].x;
-        f.y += b4.y + pf.res[it].y;
-        f.z += b4.z + pf.res[it].z;
-        f.w += b4.w + pf.res[it].w;
-      }
+      float4 b4 = pf.bias;
+      if (!rows.bb_uniform && p.bias != nullptr)  // rows of different batches in one warp tile (tiny images only)
+        b4 = __ldg(reinterpret_cast<const float4*>(p.bias + (size_t)rows.bb[it] * p.bias_bstride + n + c4));
+      f.x += b4.x + pf.res[it].x;
+      f.y += b4.y + pf.res[it].y;
+      f.z += b4.z + pf.res[it].z;
+      f.w += b4.w + pf.res[it].w;
       const uint32_t off = rows.off[it] + (uint32_t)n;
-      if constexpr (LN == 1) {
-        // producer: (sum, sum of squares) of each 16-column slot of the row -> ln_stats, and the f16 copy of the output
-        float s4 = ok ? (f.x + f.y) + (f.z + f.w) : 0.f;
-        float q4 = ok ? fmaf(f.x, f.x, f.y * f.y) + fmaf(f.z, f.z, f.w * f.w) : 0.f;
-        s4 += __shfl_xor_sync(0xffffffffu, s4, 1);
-        q4 += __shfl_xor_sync(0xffffffffu, q4, 1);
-        s4 += __shfl_xor_sync(0xffffffffu, s4, 2);
-        q4 += __shfl_xor_sync(0xffffffffu, q4, 2);
-        if (ok) {
-          if ((lane & 3) == 0) p.ln_stats[lc.srow[it] + (uint32_t)((n + c4) >> 4)] = make_float2(s4, q4);
-          __half2 a16 = __floats2half2_rn(f.x, f.y), b16 = __floats2half2_rn(f.z, f.w);
-          uint2 o16;
-          o16.x = *reinterpret_cast<uint32_t*>(&a16);
-          o16.y = *reinterpret_cast<uint32_t*>(&b16);
-          *reinterpret_cast<uint2*>(p.ln_x16 + off) = o16;
-        }
-      }
-      if (!ok) continue;
       if (p.dbg_mode == 3) {
         if (f.x == 123.456f) reinterpret_cast<float*>(p.out)[0] = f.y + f.z + f.w;  // keep the math alive, no store traffic
       } else if (p.out_f32) {
@@ -295,57 +220,11 @@ __device__ __forceinline__ void epi_linear_block(const IgemmParams& p, float* st
 }
 
 // GEGLU block: 32 value columns at taddr_v, the matching 32 gate columns at taddr_g -> 32 f16 outputs
-template <int LN>
 __device__ __forceinline__ void epi_geglu_block(const IgemmParams& p, float* stage, uint32_t taddr_v, uint32_t taddr_g, int nv,
-                                                int ng, int ncol_out, const EpiRow& me, uint32_t ok_mask, int lane, const LnCtx& lc) {
+                                                int ng, int ncol_out, const EpiRow& me, uint32_t ok_mask, int lane) {
   const int rr = lane >> 3, c4 = (lane & 7) << 2;
   const uint32_t pix_lo = (uint32_t)me.pix, pix_hi = (uint32_t)(me.pix >> 32);
   float* myrow = stage + lane * kStagePitch;
-  if constexpr (LN == 2) {
-    // LayerNorm-fold consumer: the correction needs per-column u/v, so it is applied in the coalesced mapping (one float4 of
-    // u/v per lane instead of 16 broadcast loads per row): value and gate accumulators are staged one after the other.
-    const float4 ux = __ldg(reinterpret_cast<const float4*>(p.ln_u + nv + c4)), vx = __ldg(reinterpret_cast<const float4*>(p.ln_v + nv + c4));
-    const float4 uy = __ldg(reinterpret_cast<const float4*>(p.ln_u + ng + c4)), vy = __ldg(reinterpret_cast<const float4*>(p.ln_v + ng + c4));
-    uint32_t v[32];
-    tmem_ld32(taddr_v, v);
-    tmem_ld_wait();
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      *reinterpret_cast<uint4*>(myrow + 4 * i) = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-    __syncwarp();
-    float4 xv[8];
-#pragma unroll
-    for (int it = 0; it < 8; ++it) xv[it] = *reinterpret_cast<const float4*>(stage + (it * 4 + rr) * kStagePitch + c4);
-    __syncwarp();
-    tmem_ld32(taddr_g, v);
-    tmem_ld_wait();
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      *reinterpret_cast<uint4*>(myrow + 4 * i) = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-    __syncwarp();
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int row = it * 4 + rr;
-      const size_t pix = ((size_t)__shfl_sync(0xffffffffu, pix_hi, row) << 32) | __shfl_sync(0xffffffffu, pix_lo, row);
-      if ((ok_mask >> row) & 1u) {
-        float4 y = *reinterpret_cast<const float4*>(stage + row * kStagePitch + c4);
-        float4 x = xv[it];
-        const float rs = lc.rs[it], mr = lc.mr[it];
-        x.x = fmaf(rs, x.x, fmaf(-mr, ux.x, vx.x)); x.y = fmaf(rs, x.y, fmaf(-mr, ux.y, vx.y));
-        x.z = fmaf(rs, x.z, fmaf(-mr, ux.z, vx.z)); x.w = fmaf(rs, x.w, fmaf(-mr, ux.w, vx.w));
-        y.x = fmaf(rs, y.x, fmaf(-mr, uy.x, vy.x)); y.y = fmaf(rs, y.y, fmaf(-mr, uy.y, vy.y));
-        y.z = fmaf(rs, y.z, fmaf(-mr, uy.z, vy.z)); y.w = fmaf(rs, y.w, fmaf(-mr, uy.w, vy.w));
-        __half2 a = __floats2half2_rn(x.x * gelu_erf_f(y.x), x.y * gelu_erf_f(y.y));
-        __half2 b = __floats2half2_rn(x.z * gelu_erf_f(y.z), x.w * gelu_erf_f(y.w));
-        uint2 o;
-        o.x = *reinterpret_cast<uint32_t*>(&a);
-        o.y = *reinterpret_cast<uint32_t*>(&b);
-        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + pix * p.ldo + ncol_out + c4) = o;
-      }
-    }
-    __syncwarp();
-    return;
-  }
   uint32_t v[32], g[32];
   tmem_ld32(taddr_v, v);
   tmem_ld32(taddr_g, g);
@@ -411,10 +290,8 @@ __device__ __forceinline__ void epi_linear_range(int BN, int half, int& b0, int&
 
 // Epilogue of one 128 x BN accumulator tile for one warp (32 rows, `half` selects which column blocks it owns).
 // `pf0` = prefetched operands of the warp's first LINEAR block (issued before the accumulator was complete).
-template <int LN>
 __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, float* stage, uint32_t trow, int nt, int n0,
-                                              const EpiRow& me, const EpiRows& rows, EpiPrefetch pf0, int half, int lane,
-                                              const LnCtx& lc) {
+                                              const EpiRow& me, const EpiRows& rows, EpiPrefetch pf0, int half, int lane) {
   const int BN = p.BN;
   if (p.mode == IGEMM_LINEAR) {
     if ((p.N & 15) == 0) {
@@ -428,9 +305,9 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, float* stage
         EpiPrefetch nxt = pf;
         if (bI + 1 < b1) {  // next block's operands fly while this block is transposed
           const int c2 = (bI + 1) << 5;
-          nxt = epi_prefetch<LN>(p, rows, n0 + c2, (BN - c2) >= 32 ? 32 : 16, lane);
+          nxt = epi_prefetch(p, rows, n0 + c2, (BN - c2) >= 32 ? 32 : 16, lane);
         }
-        if (n0 + c < p.N) epi_linear_block<LN>(p, stage, trow + c, n0 + c, ncols, rows, pf, lane, lc);
+        if (n0 + c < p.N) epi_linear_block(p, stage, trow + c, n0 + c, ncols, rows, pf, lane);
         pf = nxt;
       }
     } else if (half == 0) {
@@ -464,12 +341,11 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, float* stage
     const int b0 = half == 0 ? 0 : ((nb + 1) >> 1), b1 = half == 0 ? ((nb + 1) >> 1) : nb;
     for (int bI = b0; bI < b1; ++bI) {
       const int c = bI << 5;
-      epi_geglu_block<LN>(p, stage, trow + c, trow + hb + c, n0 + c, n0 + hb + c, nt * hb + c, me, ok_mask, lane, lc);
+      epi_geglu_block(p, stage, trow + c, trow + hb + c, n0 + c, n0 + hb + c, nt * hb + c, me, ok_mask, lane);
     }
   }
 }
 
-template <int LN>
 __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages x (A 16KB | B BN*128)] [full][empty][tmem_full x2][tmem_empty x2][tmem ptr]
@@ -637,20 +513,18 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         int eb0, eb1;
         epi_linear_range(BN, half, eb0, eb1);
         const int c0 = eb0 << 5;
-        if (p.mode == IGEMM_LINEAR && (p.N & 15) == 0 && eb0 < eb1) pf0 = epi_prefetch<LN>(p, rows, nt * BN + c0, (BN - c0) >= 32 ? 32 : 16, lane);
+        if (p.mode == IGEMM_LINEAR && (p.N & 15) == 0 && eb0 < eb1) pf0 = epi_prefetch(p, rows, nt * BN + c0, (BN - c0) >= 32 ? 32 : 16, lane);
         else {
 #pragma unroll
           for (int i = 0; i < 8; ++i) pf0.res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           pf0.bias = make_float4(0.f, 0.f, 0.f, 0.f);
-          pf0.u4 = pf0.v4 = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
-      const LnCtx lc = make_ln_ctx<LN>(p, me, lane);
       mbar_wait(&tmem_full[buf], (lt >> 1) & 1);
       if (dbg && lt == 0 && threadIdx.x == 64) p.dbg[3] = globaltimer_ns();  // first accumulator complete
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
-      epilogue_tile<LN>(p, stage_buf, trow, nt, nt * BN, me, rows, pf0, half, lane, lc);
+      epilogue_tile(p, stage_buf, trow, nt, nt * BN, me, rows, pf0, half, lane);
       if (dbg && lt == 0 && threadIdx.x == 64) p.dbg[4] = globaltimer_ns();  // first epilogue done
       // all TMEM reads of this buffer are complete (tcgen05.wait::ld above): hand it back to the MMA warp
       tc_fence_before();
@@ -730,7 +604,6 @@ __device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {  // arrive on `b
                : "memory");
 }
 
-template <int LN>
 __global__ void __launch_bounds__(kThreads, 1) igemm_pair_kernel(const __grid_constant__ IgemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -883,20 +756,18 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_pair_kernel(const __grid_co
         int eb0, eb1;
         epi_linear_range(BN, half, eb0, eb1);
         const int c0 = eb0 << 5;
-        if (p.mode == IGEMM_LINEAR && (p.N & 15) == 0 && eb0 < eb1) pf0 = epi_prefetch<LN>(p, rows, nt * BN + c0, (BN - c0) >= 32 ? 32 : 16, lane);
+        if (p.mode == IGEMM_LINEAR && (p.N & 15) == 0 && eb0 < eb1) pf0 = epi_prefetch(p, rows, nt * BN + c0, (BN - c0) >= 32 ? 32 : 16, lane);
         else {
 #pragma unroll
           for (int i = 0; i < 8; ++i) pf0.res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           pf0.bias = make_float4(0.f, 0.f, 0.f, 0.f);
-          pf0.u4 = pf0.v4 = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
-      const LnCtx lc = make_ln_ctx<LN>(p, me, lane);
       mbar_wait(&tmem_full[buf], (lt >> 1) & 1);
       if (dbg && lt == 0 && threadIdx.x == 64) p.dbg[3] = globaltimer_ns();  // first accumulator complete
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
-      epilogue_tile<LN>(p, stage_buf, trow, nt, nt * BN, me, rows, pf0, half, lane, lc);
+      epilogue_tile(p, stage_buf, trow, nt, nt * BN, me, rows, pf0, half, lane);
       if (dbg && lt == 0 && threadIdx.x == 64) p.dbg[4] = globaltimer_ns();  // first epilogue done
       tc_fence_before();
       __syncwarp();
@@ -1041,15 +912,23 @@ static int igemm_pick_bn_pair(int m_tiles, int N, int kblocks, int num_sms) {
   return best_bn;
 }
 
-static int device_sms() {
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms <= 0) num_sms = 148;
+// Per-device launch state: several devices may be driven from one process (one sdxl_ctx each), and the opt-in to > 48 KB of
+// dynamic shared memory, the SM count and the resident-cluster limits are all per device.
+struct IgemmDev { bool attr = false; int num_sms = 0; int max_clusters[5] = {0, 0, 0, 0, 0}; };
+static IgemmDev g_igemm_dev[64];
+static IgemmDev* igemm_dev() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  IgemmDev& D = g_igemm_dev[dev];
+  if (!D.num_sms) {
+    cudaDeviceGetAttribute(&D.num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (D.num_sms <= 0) D.num_sms = 148;
   }
-  return num_sms;
+  return &D;
+}
+static int device_sms() {
+  IgemmDev* D = igemm_dev();
+  return D ? D->num_sms : 148;
 }
 
 static size_t igemm_smem_bytes(int nst, int b_rows) {
@@ -1122,30 +1001,24 @@ int igemm_launch(cudaStream_t st, IgemmParams& p) {
   if (p.res != nullptr && p.ldr != p.ldo) return 1003;
   if ((unsigned long long)p.Bn * p.H * (unsigned long long)p.opix_row * (unsigned long long)p.ldo >= (1ull << 32)) return 1004;
   const size_t smem = igemm_smem_bytes(p.nstages, p.pair ? p.BN / 2 : p.BN);
-  if (p.ln_mode < 0 || p.ln_mode > 2) return 1005;
-  if (p.ln_mode && ((p.N & 15) || !p.ln_stats || p.ln_rows <= 0 || p.ln_slots <= 0 || (p.ln_slots & 1))) return 1006;
-  if (p.ln_mode == 1 && (unsigned long long)p.Bn * p.H * p.W * (unsigned long long)p.ln_slots >= (1ull << 32)) return 1006;
-  if (p.ln_mode == 1 && (!p.ln_x16 || !p.out_f32 || p.mode != IGEMM_LINEAR)) return 1007;
-  if (p.ln_mode == 2 && (!p.ln_u || !p.ln_v || p.ln_slots <= 0 || p.res != nullptr)) return 1008;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaSuccess;
-    const void* fns[6] = {(const void*)igemm_kernel<0>, (const void*)igemm_kernel<1>, (const void*)igemm_kernel<2>,
-                          (const void*)igemm_pair_kernel<0>, (const void*)igemm_pair_kernel<1>, (const void*)igemm_pair_kernel<2>};
-    for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  IgemmDev* D = igemm_dev();
+  if (!D) return 1009;
+  if (!D->attr) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(igemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
+    D->attr = true;
   }
   const int cs = p.CM * p.CN;
   const int m_tiles = p.tilesW * p.tilesH * p.tilesB;
   const int num_super = ((m_tiles + p.CM - 1) / p.CM) * ((p.tilesN + p.CN - 1) / p.CN);
   // resident clusters: 1 CTA per SM; cluster placement (GPC boundaries) can strand SMs for cs = 4
-  static int max_clusters[5] = {0, 0, 0, 0, 0};
+  int* max_clusters = D->max_clusters;
   if (!max_clusters[cs]) {
-    int n = device_sms() / cs;
+    int n = D->num_sms / cs;
     if (cs > 1) {
       cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3(device_sms() / cs * cs);
+      cfg.gridDim = dim3(D->num_sms / cs * cs);
       cfg.blockDim = dim3(kThreads);
       cfg.dynamicSmemBytes = 200 * 1024;
       cudaLaunchAttribute at[1];
@@ -1153,7 +1026,7 @@ int igemm_launch(cudaStream_t st, IgemmParams& p) {
       at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
       int q = 0;
-      if (cudaOccupancyMaxActiveClusters(&q, igemm_kernel<0>, &cfg) == cudaSuccess && q > 0) n = q;
+      if (cudaOccupancyMaxActiveClusters(&q, igemm_kernel, &cfg) == cudaSuccess && q > 0) n = q;
       else cudaGetLastError();
     }
     max_clusters[cs] = n;
@@ -1172,16 +1045,8 @@ int igemm_launch(cudaStream_t st, IgemmParams& p) {
     p.fd_wh = recip(m_tiles, (unsigned long long)p.tilesW * p.tilesH);
     p.fd_h = 0;
   }
-  if (p.pair) {
-    const dim3 g(nclusters * 2), b(kThreads);
-    if (p.ln_mode == 1) return launch_kernel_cluster(igemm_pair_kernel<1>, g, b, smem, st, true, 2, p);
-    if (p.ln_mode == 2) return launch_kernel_cluster(igemm_pair_kernel<2>, g, b, smem, st, true, 2, p);
-    return launch_kernel_cluster(igemm_pair_kernel<0>, g, b, smem, st, true, 2, p);
-  }
-  const dim3 g(nclusters * cs), b(kThreads);
-  if (p.ln_mode == 1) return launch_kernel_cluster(igemm_kernel<1>, g, b, smem, st, true, cs, p);
-  if (p.ln_mode == 2) return launch_kernel_cluster(igemm_kernel<2>, g, b, smem, st, true, cs, p);
-  return launch_kernel_cluster(igemm_kernel<0>, g, b, smem, st, true, cs, p);
+  if (p.pair) return launch_kernel_cluster(igemm_pair_kernel, dim3(nclusters * 2), dim3(kThreads), smem, st, true, 2, p);
+  return launch_kernel_cluster(igemm_kernel, dim3(nclusters * cs), dim3(kThreads), smem, st, true, cs, p);
 }
 
 }  // namespace sdxl

@@ -55,6 +55,22 @@ inline int launch_kernel_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block
   return (int)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// Opt-in to more than 48 KB of dynamic shared memory for `kernel`. The attribute is per DEVICE (one process may drive several
+// devices through several contexts), so call sites keep one flag per device: `static bool done[64]`.
+template <typename K>
+inline int smem_optin(K kernel, int bytes, bool (&done)[64]) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  if (dev < 0 || dev >= 64) return 2001;
+  if (!done[dev]) {
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return (int)e;
+    done[dev] = true;
+  }
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Implicit GEMM on tcgen05 (igemm.cu): out[pixel, n] = epilogue( sum_seg sum_c A_seg[pixel+tap, c] *
 // Wt[n, k(seg,c)] ). Linear layers are the 1-segment / 1x1 case of the same kernel.
@@ -92,18 +108,6 @@ struct alignas(64) IgemmParams {
   // upsample + 3x3 conv is run as four 2x2 convolutions on the original image, each writing one (row, column) parity of the
   // upsampled output: opix_row = 4W, opix_w = 2, opix_off = a*2W + b.
   int opix_row, opix_w, opix_off;
-  // LayerNorm folded into the GEMMs around it (no separate LayerNorm pass, see DESIGN.md "LayerNorm fold"):
-  //   ln_mode 1 (producer, residual GEMM whose f32 output is the next LayerNorm's input): also writes the f16 copy of the
-  //     output (the consumer's A operand) and, per row, the (sum, sum of squares) of every 16-column group of the output
-  //     into ln_stats[row * ln_slots + column / 16] (ln_slots = N / 16: independent of the tile shape);
-  //   ln_mode 2 (consumer, weights pre-multiplied by gamma): out = rstd_r * (acc - mean_r * ln_u[n]) + ln_v[n], with
-  //     mean/rstd of row r from the ln_slots partials; ln_u[n] = sum_k W'[n,k], ln_v[n] = sum_k beta_k W[n,k] + bias[n].
-  int ln_mode;
-  __half* ln_x16;             // producer: f16 copy of the output, same leading dimension as out
-  float2* ln_stats;           // [ln_rows, ln_slots] (ln_slots even, 16-byte aligned rows)
-  int ln_slots, ln_rows;
-  const float* ln_u; const float* ln_v;   // consumer, [N] (GEGLU: in the fused [value|gate] column order)
-  float ln_inv_c, ln_eps;     // consumer: 1 / (normalised width), eps
   // host-computed reciprocals (floor(2^32/d)+1; q = umulhi(n, m), exact while n*d < 2^32; 0 = use '/') for the tile-index
   // divisions of the producer warp: on the critical path between griddepcontrol.wait and the first TMA issue
   unsigned fd_pm, fd_w, fd_h, fd_wh;   // divisors: pair M tiles (or M tiles), tilesW, tilesH, tilesW*tilesH
@@ -260,10 +264,6 @@ int repack_conv_launch(cudaStream_t st, const __half* src, int O, int I, int KH,
 // read the same source pixel, added in f32, rounded once): dst [4 (a*2+b)][O][4 (th*2+tw) * Ipad].
 int repack_upconv_launch(cudaStream_t st, const __half* src, int O, int I, __half* dst, int Ipad);
 int vec_add_f32_launch(cudaStream_t st, float* dst, const float* src, int n);  // dst += src
-// LayerNorm fold into a K-major Linear weight [N, Kpad] (in place): W <- f16(gamma[k] W), u[n] = sum_k W'[n,k],
-// v[n] = sum_k beta[k] W[n,k] + bias[n] (bias nullable).
-int ln_fold_launch(cudaStream_t st, __half* W, int N, int K, int Kpad, const float* gamma, const float* beta, const float* bias,
-                   float* u, float* v);
 // bias f16 [N] -> f32, optional GEGLU permutation, optional accumulate (dst += src).
 int bias_to_f32_launch(cudaStream_t st, const __half* src, int N, float* dst, int geglu_bn, int accumulate);
 

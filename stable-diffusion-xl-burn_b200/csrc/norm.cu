@@ -247,11 +247,8 @@ int gn_launch(cudaStream_t st, GnParams& p) {
   if (nchunk > max_chunks) nchunk = max_chunks;
   p.nchunk = nchunk;
   const size_t smem1 = (size_t)R * C * 2 * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    attr = true;
-  }
+  static bool optin[64];
+  if (int r = smem_optin(gn_stats_kernel, 160 * 1024, optin)) return r;
   float* fin = gn_final(p.partial, p.B, p.n_group);
   unsigned* cnt = gn_counters(p.partial, p.B, p.n_group);
   int e = launch_kernel(gn_stats_kernel, dim3(nchunk, p.B), dim3(V * R), smem1, st, true, p.x1, p.C1, p.x2, p.C2, p.HW,

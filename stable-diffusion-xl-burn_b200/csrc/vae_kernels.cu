@@ -80,12 +80,8 @@ int softmax_rows_launch(cudaStream_t st, const float* S, size_t lds, int rows, i
   const size_t smem = (size_t)cols * sizeof(float);
   const int cache = smem <= 160 * 1024;
   if (cache && smem > 48 * 1024) {
-    static bool done = false;
-    if (!done) {
-      cudaError_t e = cudaFuncSetAttribute(softmax_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-      if (e != cudaSuccess) return (int)e;
-      done = true;
-    }
+    static bool optin[64];
+    if (int r = smem_optin(softmax_rows_kernel, 160 * 1024, optin)) return r;
   }
   const float sl2e = scale * 1.4426950408889634f;
   return launch_kernel(softmax_rows_kernel, dim3(rows), dim3(kSoftmaxThreads), cache ? smem : 0, st, true, S, lds, cols, sl2e,

@@ -77,8 +77,10 @@ PROTOTYPES = {
     "sdxl_sampler_set_latent": (I, [P, P, I]),
     "sdxl_sampler_get_latent": (I, [P, P, I]),
     "sdxl_unet_alpha": (C.c_double, [P, I]),
+    "sdxl_unet_load_broadcast": (I, [P, C.POINTER(UnetCfg), P, C.c_size_t, I, P, I, I, C.POINTER(P)]),
     "sdxl_unet_plan_flops": (C.c_double, [P]),
     "sdxl_unet_plan_num_ops": (I, [P]),
+    "sdxl_unet_plan_flops_executed": (C.c_double, [P]),
     "sdxl_unet_profile_plan": (I, [P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "sdxl_unet_profile_dump": (I, [P, C.c_char_p]),
     "sdxl_dbg_igemm_timeline": (I, [P, I, I, I, I, I, C.POINTER(C.c_uint64)]),

@@ -235,18 +235,27 @@ def _cfg_struct(cfg: UNetConfig) -> _lib.UnetCfg:
 class Diffuser:
     """Mirror of the reference's Diffuser (UNet + alphas + sampler loops), device-resident."""
 
-    def __init__(self, ctx: Context, cfg: UNetConfig, weights):
-        """weights: dict name->f16 tensor (reference layouts) or an already-built pack (uint8 tensor)."""
+    def __init__(self, ctx: Context, cfg: UNetConfig, weights, nccl_comm=None, rank: int = 0, root: int = 0):
+        """weights: dict name->f16 tensor (reference layouts) or an already-built pack (uint8 tensor).
+        nccl_comm (an ncclComm_t, see sharding.nccl_comm_init): multi-GPU load through sdxl_unet_load_broadcast — only `root`
+        passes weights, every other rank passes None and receives the pack over NCCL inside the library."""
         self.ctx, self.cfg = ctx, cfg
-        pack = weights if isinstance(weights, torch.Tensor) else build_pack(weights)
-        on_device = pack.is_cuda
+        h = C.c_void_p()
+        cs = _cfg_struct(cfg)
+        pack = None
+        if weights is not None:
+            pack = weights if isinstance(weights, torch.Tensor) else build_pack(weights)
+        on_device = bool(pack is not None and pack.is_cuda)
         ctx.enter()
         if on_device:
             torch.cuda.current_stream(ctx.device).synchronize()
-        h = C.c_void_p()
-        cs = _cfg_struct(cfg)
-        rc = ctx.lib.sdxl_unet_load(ctx.h, C.byref(cs), pack.data_ptr(), pack.numel(), int(on_device), C.byref(h))
-        ctx.check(rc, "sdxl_unet_load")
+        if nccl_comm is not None:
+            rc = ctx.lib.sdxl_unet_load_broadcast(ctx.h, C.byref(cs), None if pack is None else pack.data_ptr(),
+                                                  0 if pack is None else pack.numel(), int(on_device), nccl_comm, rank, root, C.byref(h))
+            ctx.check(rc, "sdxl_unet_load_broadcast")
+        else:
+            rc = ctx.lib.sdxl_unet_load(ctx.h, C.byref(cs), pack.data_ptr(), pack.numel(), int(on_device), C.byref(h))
+            ctx.check(rc, "sdxl_unet_load")
         self.h = h
         self._cond_key = None
         self._keep = None
@@ -299,6 +308,10 @@ class Diffuser:
     @property
     def plan_flops(self) -> float:
         return float(self.ctx.lib.sdxl_unet_plan_flops(self.h))
+
+    @property
+    def plan_flops_executed(self) -> float:
+        return float(self.ctx.lib.sdxl_unet_plan_flops_executed(self.h))
 
     @property
     def plan_num_ops(self) -> int:

@@ -44,3 +44,40 @@ def gather_latents(latent: torch.Tensor) -> List[torch.Tensor]:
     out = [torch.empty_like(latent) for _ in range(dist.get_world_size())]
     dist.all_gather(out, latent)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# NCCL communicator for the C ABI's own multi-GPU load (sdxl_unet_load_broadcast)
+# ---------------------------------------------------------------------------------------------------
+class _NcclUniqueId(__import__("ctypes").Structure):
+    _fields_ = [("internal", __import__("ctypes").c_char * 128)]
+
+
+def nccl_comm_init(rank: int, world: int, device: torch.device):
+    """Creates an ncclComm_t (returned as a ctypes void pointer) the way a non-Python host would: ncclGetUniqueId on rank 0,
+    the 128-byte id shared through the already-initialised torch.distributed group (any backend), ncclCommInitRank on every
+    rank. The handle is what `sdxl_unet_load_broadcast` takes; call nccl_comm_destroy when done."""
+    import ctypes as C
+    lib = C.CDLL("libnccl.so.2")   # the copy torch already loaded
+    uid = _NcclUniqueId()
+    if rank == 0:
+        rc = lib.ncclGetUniqueId(C.byref(uid))
+        if rc != 0:
+            raise RuntimeError(f"ncclGetUniqueId failed with {rc}")
+    box = [C.string_at(C.byref(uid), 128) if rank == 0 else None]   # all 128 bytes (a c_char array read stops at the first NUL)
+    dist.broadcast_object_list(box, src=0)
+    C.memmove(C.byref(uid), box[0], 128)
+    torch.cuda.set_device(device)
+    comm = C.c_void_p()
+    lib.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, _NcclUniqueId, C.c_int]
+    rc = lib.ncclCommInitRank(C.byref(comm), world, uid, rank)
+    if rc != 0:
+        raise RuntimeError(f"ncclCommInitRank failed with {rc}")
+    return comm
+
+
+def nccl_comm_destroy(comm) -> None:
+    import ctypes as C
+    lib = C.CDLL("libnccl.so.2")
+    lib.ncclCommDestroy.argtypes = [C.c_void_p]
+    lib.ncclCommDestroy(comm)

@@ -72,3 +72,77 @@ def test_text_to_image_and_inpaint(ctx):
     assert out.shape == (1, 4, 8, 8) and torch.isfinite(out).all()
     for o in (ea, eb, dif, vae):
         o.close()
+
+
+def test_unet_load_broadcast_two_gpus():
+    """sdxl_unet_load_broadcast at world size 2 (one rank per GPU, torchrun): needs two devices."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29577", os.path.join(root, "tests", "mp", "load_broadcast.py")], cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "LOAD_BROADCAST_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+
+
+def _tiny_forward_inputs(seed):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(2, 4, 16, 16, generator=g), torch.randn(2, 5, TINY.context_dim, generator=g).half().float(),
+            torch.randn(2, TINY.adm_in_channels, generator=g).half().float())
+
+
+def test_two_contexts_two_threads():
+    """include/sdxl_b200.h: "one sdxl_ctx per (device, stream) ... independent ctxs are fully concurrent". Two contexts on one
+    device, two models, driven from two host threads at once (ctypes releases the GIL): every result equals the sequential one
+    bit for bit (no process-global mutable state on the path)."""
+    import threading
+    import sdxl_b200
+    ctxs = [sdxl_b200.Context(0) for _ in range(2)]
+    ds = [Diffuser(c, TINY, synth_weights(TINY, seed=s)) for c, s in zip(ctxs, (0, 1))]
+    ins = [_tiny_forward_inputs(10), _tiny_forward_inputs(11)]
+    ts = [[999, 500, 1], [250, 749, 3]]
+    seq = [[ds[i].unet_forward(ins[i][0], [t], ins[i][1], ins[i][2]).cpu() for t in ts[i]] for i in range(2)]
+    out = [[None] * 3, [None] * 3]
+    errors = []
+
+    def work(i):
+        try:
+            torch.cuda.set_device(0)
+            for rep in range(5):
+                for k, t in enumerate(ts[i]):
+                    out[i][k] = ds[i].unet_forward(ins[i][0], [t], ins[i][1], ins[i][2]).cpu()
+        except Exception as ex:  # noqa: BLE001
+            errors.append(ex)
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errors, errors
+    for i in range(2):
+        for k in range(3):
+            assert torch.equal(out[i][k], seq[i][k])
+    for d in ds:
+        d.close()
+    for c in ctxs:
+        c.close()
+
+
+def test_two_devices_one_process():
+    """Per-device launch state (shared-memory opt-in, SM count, cluster occupancy): a second device in the same process works."""
+    import sdxl_b200
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    w = synth_weights(TINY, seed=0)
+    x, c, y = _tiny_forward_inputs(12)
+    ref = O.unet_forward(TINY, O.to_f32(w), x, torch.tensor([400]), c, y)
+    for dev in (0, 1, 0):
+        ctx = sdxl_b200.Context(dev)
+        d = Diffuser(ctx, TINY, w)
+        out = d.unet_forward(x, [400], c, y).cpu()
+        e = float((out - ref).norm() / ref.norm())
+        print(f"device {dev}: tiny forward rel err {e:.3e}")
+        assert e < 2e-3
+        d.close()
+        ctx.close()
