@@ -310,6 +310,20 @@ SDXL_API int sdxl_clip_forward_hidden_pooled(sdxl_clip* clip, int B, const int32
                                              float* hidden_out, float* pooled_out, int out_on_host);
 SDXL_API double sdxl_clip_plan_flops(const sdxl_clip* clip);
 
+/* ---- `sample` front-end helpers --------------------------------------------------------------------- */
+/* Inpainting mask from a crop window in pixels (src/bin/sample/main.rs:144-190): latent coordinates = pixel / (img_h / lat_h),
+ * ones inside the window, zero outside, inverted by crop_out; mask = 1 keeps the generated latent. Negative bound = not given
+ * (0 / image extent). Output: host uint8 [n_channels, lat_h, lat_w] (the [1,4,h,w] Bool tensor of the reference). */
+SDXL_API int sdxl_make_inpaint_mask(int img_w, int img_h, int lat_w, int lat_h, int crop_left, int crop_right, int crop_top,
+                                    int crop_bottom, int crop_out, int n_channels, uint8_t* mask_out_host);
+
+/* ---- burn record (.mpk) helper ----------------------------------------------------------------------- */
+/* The reference ships weights as burn 0.13 NamedMpkFileRecorder<HalfPrecisionSettings> records (src/bin/convert/main.rs:65-70,
+ * loaded at src/bin/sample/main.rs:28-51): MessagePack, tensors as {"value": [f16 bit patterns as msgpack uints], "shape": [..]}.
+ * sdxl_b200/burn_record.py walks the tree; these decode / encode the value arrays (host memory, no CUDA). */
+SDXL_API int sdxl_mpk_decode_u16(const uint8_t* buf, size_t len, size_t count, uint16_t* out, size_t* consumed);
+SDXL_API size_t sdxl_mpk_encode_u16(const uint16_t* in, size_t count, uint8_t* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -341,6 +341,22 @@ def refine_latent(cfg, w, alphas, latent, c, guidance, step_start, n_steps, nois
     return diffuse_latent(cfg, w, alphas, noised, c, step_start, n_steps, guidance)
 
 
+def make_inpaint_mask(img_w: int, img_h: int, lat_w: int, lat_h: int, crop_left: Optional[int], crop_right: Optional[int],
+                      crop_top: Optional[int], crop_bottom: Optional[int], crop_out: bool) -> torch.Tensor:
+    """The `sample` binary's mask, src/bin/sample/main.rs:144-190: ones [crop_h, crop_w] padded with zeros to the latent extent,
+    Bool, expanded to [1, 4, h, w], inverted by --crop-out."""
+    crop_left = 0 if crop_left is None else crop_left                # :144-147
+    crop_right = img_w if crop_right is None else crop_right
+    crop_top = 0 if crop_top is None else crop_top
+    crop_bottom = img_h if crop_bottom is None else crop_bottom
+    scale = img_h // lat_h                                          # :164
+    crop_left, crop_right, crop_top, crop_bottom = crop_left // scale, crop_right // scale, crop_top // scale, crop_bottom // scale   # :165-168
+    ones = torch.ones(crop_bottom - crop_top, crop_right - crop_left)
+    mask = F.pad(ones, (crop_left, lat_w - crop_right, crop_top, lat_h - crop_bottom), value=0.0).bool()   # :177-179
+    mask = mask.unsqueeze(0).unsqueeze(0).expand(1, 4, lat_h, lat_w)
+    return ~mask if crop_out else mask                               # :183-187
+
+
 def n_iterations(n_steps: int, step_start: int = 0, total: int = 1000) -> int:
     """ceil((total - step_start) / floor(total / n_steps)) — SURVEY D6/D7."""
     step = total // n_steps

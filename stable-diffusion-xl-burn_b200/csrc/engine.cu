@@ -1073,6 +1073,34 @@ extern "C" int sdxl_sample_latent(sdxl_unet* u, const sdxl_conditioning* cond, d
   return 0;
 }
 
+// ================================================================================================
+// inpainting mask of the `sample` front end (reference src/bin/sample/main.rs:144-190)
+// ================================================================================================
+// Crop window in PIXELS -> Bool mask [1, n_channels, h/8... ] in latent coordinates: pixel coordinates are divided by
+// scale = image height / latent height (integer division, main.rs:164-169), ones inside [top,bottom) x [left,right), zero padding
+// outside, inverted by crop_out (main.rs:183-187). mask = 1 keeps the GENERATED latent (mask_where, stablediffusion/mod.rs:465).
+// A negative bound means "not given" (the reference's Option defaults: 0 / image extent). Host memory, [n_channels, lat_h, lat_w].
+extern "C" int sdxl_make_inpaint_mask(int img_w, int img_h, int lat_w, int lat_h, int crop_left, int crop_right, int crop_top,
+                                      int crop_bottom, int crop_out, int n_channels, uint8_t* mask_out_host) {
+  if (!mask_out_host || img_w <= 0 || img_h <= 0 || lat_w <= 0 || lat_h <= 0 || n_channels <= 0 || lat_h > img_h) return -1;
+  const int l = crop_left < 0 ? 0 : crop_left, r = crop_right < 0 ? img_w : crop_right;
+  const int t = crop_top < 0 ? 0 : crop_top, b = crop_bottom < 0 ? img_h : crop_bottom;
+  // the reference asserts `right <= w && bottom <= h && left < right || top < bottom` (operator precedence makes it weaker than
+  // intended); here every condition must hold
+  if (r > img_w || b > img_h || l >= r || t >= b) return 5500;
+  const int scale = img_h / lat_h;
+  if (scale <= 0) return 5501;
+  const int cl = l / scale, cr = r / scale, ct = t / scale, cb = b / scale;
+  if (cr > lat_w || cb > lat_h) return 5502;
+  for (int c = 0; c < n_channels; ++c)
+    for (int y = 0; y < lat_h; ++y)
+      for (int x = 0; x < lat_w; ++x) {
+        const bool inside = y >= ct && y < cb && x >= cl && x < cr;
+        mask_out_host[((size_t)c * lat_h + y) * lat_w + x] = (uint8_t)(inside != (crop_out != 0));
+      }
+  return 0;
+}
+
 extern "C" void sdxl_unet_destroy(sdxl_unet* u) {
   if (!u) return;
   cudaStreamSynchronize(u->ctx->stream);

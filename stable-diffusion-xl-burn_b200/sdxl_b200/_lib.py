@@ -115,6 +115,9 @@ PROTOTYPES = {
     "sdxl_clip_forward_hidden": (I, [P, I, C.POINTER(C.c_int32), I, P, I]),
     "sdxl_clip_forward_hidden_pooled": (I, [P, I, C.POINTER(C.c_int32), I, P, P, I]),
     "sdxl_clip_plan_flops": (C.c_double, [P]),
+    "sdxl_make_inpaint_mask": (I, [I, I, I, I, I, I, I, I, I, I, P]),
+    "sdxl_mpk_decode_u16": (I, [P, C.c_size_t, C.c_size_t, P, C.POINTER(C.c_size_t)]),
+    "sdxl_mpk_encode_u16": (C.c_size_t, [P, C.c_size_t, P]),
 }
 
 PROFILE_KINDS = 24   # SDXL_PROFILE_KINDS (include/sdxl_b200.h)

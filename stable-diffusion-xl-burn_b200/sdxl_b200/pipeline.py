@@ -1,0 +1,47 @@
+"""The `sample` binary's flow (reference src/bin/sample/main.rs:128-285) over the library: crop window -> inpainting mask,
+text -> conditioning -> base sampling (plain or inpainting) -> optional refiner hand-off -> latent -> image."""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+REFINER_STEP_START = 800   # main.rs:263: the refiner re-noises to t0 = 1000 - 800 and runs the remaining iterations
+
+
+def make_inpaint_mask(img_hw: Tuple[int, int], latent_hw: Tuple[int, int], crop_left: Optional[int] = None, crop_right: Optional[int] = None,
+                      crop_top: Optional[int] = None, crop_bottom: Optional[int] = None, crop_out: bool = False, n_channels: int = 4) -> torch.Tensor:
+    """== main.rs:144-190 (sdxl_make_inpaint_mask). Returns Bool [1, n_channels, h, w]; True keeps the generated latent."""
+    lib = _lib.load()
+    (ih, iw), (lh, lw) = img_hw, latent_hw
+    out = np.empty((n_channels, lh, lw), dtype=np.uint8)
+    opt = lambda v: -1 if v is None else int(v)  # noqa: E731
+    rc = lib.sdxl_make_inpaint_mask(iw, ih, lw, lh, opt(crop_left), opt(crop_right), opt(crop_top), opt(crop_bottom), int(crop_out), n_channels, out.ctypes.data)
+    if rc != 0:
+        raise _lib.SdxlError(f"sdxl_make_inpaint_mask failed with {rc}: invalid crop parameters")
+    return torch.from_numpy(out).bool().unsqueeze(0)
+
+
+def sample(embedder, diffuser, decoder, prompt: str, guidance: float = 7.5, n_steps: int = 30, refiner=None,
+           reference_rgb: Optional[torch.Tensor] = None, crop: Sequence[Optional[int]] = (None, None, None, None), crop_out: bool = False,
+           resolution: Tuple[int, int] = (1024, 1024), seed: int = 0, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One image, like `sample --prompt ... [--reference-img ... --crop-* ...] [--use-refiner]`.
+    reference_rgb: uint8 [1, H, W, 3] (the reference image: switches to inpainting, main.rs:131-197); crop = (left, right, top,
+    bottom) in pixels. Returns uint8 [1, H, W, 3]."""
+    if reference_rgb is not None:
+        resolution = (int(reference_rgb.shape[1]), int(reference_rgb.shape[2]))        # main.rs:225-229: orig_dims
+    size = [int(resolution[0]), int(resolution[1])]
+    cond = embedder.text_to_conditioning(prompt, size, [0, 0], size)                     # main.rs:231-235: size, crop = 0, ar = size
+    if reference_rgb is not None:
+        ref_latent = decoder.image_to_latent(reference_rgb)                              # main.rs:158
+        lh, lw = int(ref_latent.shape[2]), int(ref_latent.shape[3])
+        mask = make_inpaint_mask(resolution, (lh, lw), *crop, crop_out=crop_out)
+        latent = diffuser.sample_latent_with_inpainting(cond, guidance, n_steps, ref_latent, mask, init_noise=noise, seed=seed)   # main.rs:246
+    else:
+        latent = diffuser.sample_latent(cond, guidance, n_steps, noise=noise, seed=seed)                                      # main.rs:249
+    if refiner is not None:
+        latent = refiner.refine_latent(latent, cond, guidance, REFINER_STEP_START, n_steps, seed=seed + 1)                    # main.rs:258-265
+    return decoder.latent_to_image(latent)                                                                                   # main.rs:277

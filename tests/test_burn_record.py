@@ -1,0 +1,101 @@
+"""The reference's shipped weight format (burn 0.13 NamedMpkFileRecorder<HalfPrecisionSettings> `.mpk` + `.cfg`, reference
+src/bin/convert/main.rs:65-70, src/bin/sample/main.rs:28-51) and the `sample` front-end's inpainting mask
+(src/bin/sample/main.rs:144-190). CPU only: the library's host-side helpers, no CUDA call."""
+import json
+import os
+
+import msgpack
+import numpy as np
+import pytest
+import torch
+
+import sdxl_b200
+from sdxl_b200 import TINY, TINY_REFINER, burn_record as BR, synth_weights
+from oracle import unet_oracle as O
+
+
+def test_value_array_codec_matches_msgpack():
+    """The native u16 array codec against the `msgpack` package on every encoding class (fixint, uint8, uint16)."""
+    import ctypes as C
+    lib = sdxl_b200.load()
+    vals = np.array([0, 1, 127, 128, 200, 255, 256, 0x3C00, 0xFFFF, 0x7BFF, 5] + list(np.random.default_rng(0).integers(0, 65536, 5000)), dtype=np.uint16)
+    buf = np.empty(3 * vals.size, dtype=np.uint8)
+    n = lib.sdxl_mpk_encode_u16(vals.ctypes.data, vals.size, buf.ctypes.data)
+    ref = b"".join(msgpack.packb(int(v)) for v in vals)
+    assert buf[:n].tobytes() == ref
+    out = np.empty_like(vals)
+    used = C.c_size_t(0)
+    assert lib.sdxl_mpk_decode_u16(buf.ctypes.data, n, vals.size, out.ctypes.data, C.byref(used)) == 0
+    assert used.value == n and np.array_equal(out, vals)
+    assert lib.sdxl_mpk_decode_u16(buf.ctypes.data, n - 1, vals.size, out.ctypes.data, C.byref(used)) == 7001   # truncated
+    bad = np.frombuffer(msgpack.packb(-3), dtype=np.uint8).copy()
+    assert lib.sdxl_mpk_decode_u16(bad.ctypes.data, bad.size, 1, out.ctypes.data, C.byref(used)) == 7003          # not unsigned
+
+
+@pytest.mark.parametrize("cfg,seed", [(TINY, 0), (TINY_REFINER, 1)])
+def test_diffuser_record_round_trip(tmp_path, cfg, seed):
+    """weights -> <name>.mpk + <name>.cfg -> weights: bit-identical tensors, identical config; the file is a MessagePack document
+    the `msgpack` package reads, with the record layout burn's NamedMpk recorder writes (metadata + item, fields by name, enum
+    blocks as one-entry maps, constants as nil, f16 bit patterns as unsigned integers)."""
+    w = synth_weights(cfg, seed=seed)
+    path = str(tmp_path / "diffuser")
+    BR.save_diffuser(path, cfg, w)
+    cfg2, w2 = BR.load_diffuser(path)
+    assert cfg2 == cfg
+    assert set(w2) == set(w)
+    for k in w:
+        assert w2[k].dtype == torch.float16 and torch.equal(w2[k], w[k]), k
+    # independent reader: the msgpack package sees the same tree
+    with open(path + ".mpk", "rb") as fh:
+        doc = msgpack.unpackb(fh.read(), raw=False, strict_map_key=True)
+    assert doc["metadata"]["float"] == "f16" and doc["metadata"]["version"].startswith("0.13")
+    item = doc["item"]
+    assert set(item) == {"n_steps", "alpha_cumulative_products", "diffusion", "is_refiner"} and item["n_steps"] is None
+    blk0 = item["diffusion"]["input_blocks"][0]
+    assert list(blk0) == ["Conv"] and blk0["Conv"]["weight"]["param"]["shape"] == [cfg.model_channels, cfg.in_channels, 3, 3]
+    lin = item["diffusion"]["lin1_time_embed"]["weight"]["param"]
+    assert lin["shape"] == [cfg.model_channels, 4 * cfg.model_channels]                       # burn Linear weight is [d_input, d_output]
+    got = np.array(lin["value"], dtype=np.uint16).view(np.float16).reshape(lin["shape"])
+    assert np.array_equal(got, w["lin1_time_embed/weight"].numpy())
+    kinds = [list(b)[0] for b in item["diffusion"]["output_blocks"]]
+    assert kinds[2] in ("ResTU", "ResU") and set(kinds) <= {"Res", "ResT", "ResTU", "ResU"}
+    # the .cfg is the DiffuserConfig JSON (stablediffusion/mod.rs:269-278)
+    d = json.load(open(path + ".cfg"))
+    assert d["num_head_channels"] == 64 and d["is_refiner"] == cfg.is_refiner and d["channel_mults"] == list(cfg.channel_mults)
+
+
+def test_record_reader_rejects_damage(tmp_path):
+    w = synth_weights(TINY, seed=0)
+    path = str(tmp_path / "d")
+    BR.save_diffuser(path, TINY, w)
+    raw = open(path + ".mpk", "rb").read()
+    open(path + ".mpk", "wb").write(raw[: len(raw) // 2])
+    with pytest.raises(BR.BurnRecordError):
+        BR.load_diffuser(path)
+    open(path + ".mpk", "wb").write(msgpack.packb({"hello": 1}))
+    with pytest.raises(BR.BurnRecordError):
+        BR.load_diffuser(path)
+    os.remove(path + ".cfg")
+    with pytest.raises(FileNotFoundError):
+        BR.load_diffuser(path)
+
+
+@pytest.mark.parametrize("img,crop,crop_out", [((1024, 1024), (None, None, None, 200), False), ((1024, 1024), (100, 731, 37, 999), False),
+                                               ((1024, 1024), (100, 731, 37, 999), True), ((768, 1344), (8, 1344, 0, 768), False),
+                                               ((1024, 1024), (0, 7, 0, 1024), False), ((1152, 896), (3, 893, 5, 1150), True)])
+def test_inpaint_mask_matches_oracle(img, crop, crop_out):
+    """sdxl_make_inpaint_mask against the restated reference (src/bin/sample/main.rs:144-190), bit for bit."""
+    h, w = img
+    lat = (h // 8, w // 8)
+    ref = O.make_inpaint_mask(w, h, lat[1], lat[0], crop[0], crop[1], crop[2], crop[3], crop_out)
+    got = sdxl_b200.make_inpaint_mask(img, lat, *crop, crop_out=crop_out)
+    assert got.dtype == torch.bool and got.shape == (1, 4, lat[0], lat[1])
+    assert torch.equal(got, ref)
+    if crop == (None, None, None, 200) and not crop_out:
+        assert got[0, 0, :25].all() and not got[0, 0, 25:].any()          # BASELINE config 5: rows 0..25 (200 px / 8)
+
+
+def test_inpaint_mask_rejects_bad_windows():
+    for crop in ((10, 5, 0, 100), (0, 2000, 0, 100), (0, 100, 50, 50)):
+        with pytest.raises(sdxl_b200.SdxlError):
+            sdxl_b200.make_inpaint_mask((1024, 1024), (128, 128), *crop)

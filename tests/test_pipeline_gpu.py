@@ -70,6 +70,26 @@ def test_text_to_image_and_inpaint(ctx):
     mask[:, :, :3] = True
     out = dif.sample_latent_with_inpainting(cond, 5.0, 6, ref_lat, mask, seed=7)
     assert out.shape == (1, 4, 8, 8) and torch.isfinite(out).all()
+
+    # the `sample` flow as one call (sdxl_b200.pipeline.sample == main.rs:128-285): same latent path -> same image; the inpainting
+    # branch builds the mask from the crop window (here rows 0..24 px = latent rows 0..3 of 8: scale = 32 / 8 = 4)
+    import sdxl_b200
+    img2 = sdxl_b200.sample(emb, dif, vae, text, guidance=5.0, n_steps=6, resolution=res, noise=noise)
+    assert torch.equal(img2, rgb)
+    m = sdxl_b200.make_inpaint_mask((32, 32), (8, 8), None, None, None, 12)
+    assert torch.equal(m, mask)
+    img3 = sdxl_b200.sample(emb, dif, vae, text, guidance=5.0, n_steps=6, reference_rgb=ref_rgb, crop=(None, None, None, 12), seed=7)
+    assert img3.shape == (1, 32, 32, 3) and img3.dtype == torch.uint8
+
+    # the reference's shipped format: <name>.mpk + <name>.cfg -> Diffuser, bit-identical to the direct load
+    import tempfile
+    from sdxl_b200 import burn_record as BR
+    with tempfile.TemporaryDirectory() as td:
+        BR.save_diffuser(os.path.join(td, "diffuser"), UNET, wu)
+        cfg2, w2 = BR.load_diffuser(os.path.join(td, "diffuser"))
+    dif2 = Diffuser(ctx, cfg2, w2)
+    assert torch.equal(dif2.sample_latent(cond, 5.0, 6, noise=noise), latent)
+    dif2.close()
     for o in (ea, eb, dif, vae):
         o.close()
 
