@@ -126,7 +126,11 @@ __device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
 // ------------------------------------------------------------------------------------------------
 static constexpr int kStagePitch = 36;                                   // words
 static constexpr int kStageBytesPerWarp = 32 * kStagePitch * 4;           // 4608 B
-static constexpr int kEpiStageBytes = kEpiWarps * kStageBytesPerWarp;     // 36864 B
+static constexpr int kEpiStageBytes = kEpiWarps * kStageBytesPerWarp;     // 36864 B (transposing epilogue)
+static constexpr int kEpiTmaBufBytes = 4096;                               // one 32-row x 128-byte box
+static constexpr int kEpiAreaBytes = kEpiWarps * 2 * kEpiTmaBufBytes;      // 65536 B: two boxes per epilogue warp (TMA epilogue); the
+                                                                          // transposing epilogue uses the first kEpiStageBytes of it
+static_assert(kEpiStageBytes <= kEpiAreaBytes, "staging area too small");
 
 struct EpiRow {          // per-lane description of "my" accumulator row (lane = row within the warp's 32 rows)
   size_t pix;            // pixel (row of the output matrix)
@@ -261,6 +265,132 @@ __device__ __forceinline__ void epi_geglu_block(const IgemmParams& p, float* sta
   __syncwarp();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Epilogue through TMA (LINEAR tiles whose 128 rows are contiguous rows of a plain [pixels, ldo] output; N, BN multiples of 32).
+// The transposing epilogue above costs ~5 us per 128 x 160 f32 tile (per-thread global loads / stores behind a smem transpose),
+// more than the main loop of the 372 single-wave transformer GEMMs of a step. Here no thread touches global memory:
+//   * the f32 residual box (32 rows x 32 columns = 32 x 128 B) of a warp's next column block is fetched by TMA into a 128B-swizzled
+//     smem box while the current block is processed (the first one while the MMAs of the tile still run);
+//   * every lane owns one row: TMEM -> registers, + bias + residual (its own 128 B of the box, conflict-free 16-byte chunks
+//     through the swizzle), result written IN PLACE;
+//   * one TMA store per box (fence.proxy.async, lane 0), two boxes per warp so that the store of block b overlaps block b + 1.
+// f16 outputs (no residual) use 32-row x 64-byte boxes with the 64B swizzle.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src_smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+               "r"(src_smem), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_group_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_2d_u32(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts128u(uint32_t a, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// per-warp state of the TMA epilogue; `kb` counts this warp's column blocks over the whole kernel (box = kb & 1)
+struct EpiTma {
+  uint32_t box[2];      // smem addresses of the warp's two boxes (1024 B aligned)
+  uint32_t bar[2];      // mbarriers of the residual loads
+  uint32_t kb;
+};
+// request the residual box of column block `n` (rows row0 .. row0 + 31) into the box that block `kb_of_block` will use. Lane 0 only.
+__device__ __forceinline__ void epi_tma_request_res(const IgemmParams& p, const EpiTma& e, uint32_t kb_of_block, int n, int row0) {
+  const uint32_t b = kb_of_block & 1u;
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(e.bar[b]), "r"((uint32_t)kEpiTmaBufBytes) : "memory");
+  tma_load_2d_u32(e.box[b], &p.tmRes, e.bar[b], n, row0);
+}
+// One tile for one warp: column blocks [b0, b1) of the tile (32 columns each), rows row0 .. row0 + 31 of the output matrix.
+// The residual of block b0 has been requested by the caller (epi_tma_request_res) before the accumulator was complete.
+__device__ __forceinline__ void epilogue_tile_tma(const IgemmParams& p, EpiTma& e, uint32_t trow, int n0, int b0, int b1, int row0, int bb,
+                                                  bool row_ok, int lane) {
+  const bool has_res = p.res != nullptr;
+  const float* bias_row = p.bias ? p.bias + (size_t)bb * p.bias_bstride : nullptr;
+  for (int bI = b0; bI < b1; ++bI) {
+    const int n = n0 + (bI << 5);
+    const uint32_t cur = e.kb & 1u;
+    if (lane == 0) {
+      // the box block kb+1 will use was last read by the store of block kb-1: that read must be over before it is refilled / rewritten
+      if (has_res) {
+        bulk_wait_group_read<0>();
+        if (bI + 1 < b1) epi_tma_request_res(p, e, e.kb + 1, n + 32, row0);
+      } else {
+        bulk_wait_group_read<1>();   // this block's own box: last read by the store of block kb-2
+      }
+    }
+    float4 bs[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bs[j] = bias_row ? __ldg(reinterpret_cast<const float4*>(bias_row + n) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t v[32];
+    tmem_ld32(trow + (bI << 5), v);
+    tmem_ld_wait();
+    __syncwarp();   // lane 0's wait above covers the whole warp's writes into the box
+    if (has_res) {
+      // residual box landed? (parity: this box's barrier completes once per use of the box)
+      const uint32_t parity = (e.kb >> 1) & 1u;
+      uint32_t ok = 0;
+      for (uint32_t spin = 0; !ok; ++spin) {   // bounded: a protocol bug must trap, not hang the GPU
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(e.bar[cur]), "r"(parity) : "memory");
+        if (!ok && spin > (1u << 24)) {
+          printf("sdxl_b200: igemm residual box wait timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+          __trap();
+        }
+      }
+    }
+    if (p.out_f32) {
+      const uint32_t rowa = e.box[cur] + (uint32_t)lane * 128u;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t a = rowa + ((uint32_t)(j ^ (lane & 7)) << 4);   // SWIZZLE_128B: 16-byte chunk j of row r sits at j ^ (r & 7)
+        float4 o = make_float4(__uint_as_float(v[4 * j]) + bs[j].x, __uint_as_float(v[4 * j + 1]) + bs[j].y,
+                               __uint_as_float(v[4 * j + 2]) + bs[j].z, __uint_as_float(v[4 * j + 3]) + bs[j].w);
+        if (has_res) {
+          const float4 r = lds128(a);
+          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        sts128(a, o);
+      }
+    } else {
+      const uint32_t rowa = e.box[cur] + (uint32_t)lane * 64u;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t a = rowa + ((uint32_t)(j ^ ((lane >> 1) & 3)) << 4);   // SWIZZLE_64B: chunk j of row r sits at j ^ ((r >> 1) & 3)
+        uint32_t h[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 b4 = bs[2 * j + (i >> 1)];
+          const float bx = (i & 1) ? b4.z : b4.x, by = (i & 1) ? b4.w : b4.y;
+          __half2 t = __floats2half2_rn(__uint_as_float(v[8 * j + 2 * i]) + bx, __uint_as_float(v[8 * j + 2 * i + 1]) + by);
+          h[i] = *reinterpret_cast<uint32_t*>(&t);
+        }
+        sts128u(a, make_uint4(h[0], h[1], h[2], h[3]));
+      }
+    }
+    (void)row_ok;   // rows past the end of the output are clipped by the tensor map
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(&p.tmOut, e.box[cur], n, row0);
+      bulk_commit_group();
+    }
+    ++e.kb;
+  }
+}
+
 // phase-2 row descriptors from the per-lane (lane = row) description
 __device__ __forceinline__ EpiRows epi_rows(const EpiRow& me, int ld, int lane) {
   EpiRows r;
@@ -353,12 +483,14 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   const int BN = p.BN;
   const int nst = p.nstages;
   const uint32_t stage_bytes = kABytes + BN * 128;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)nst * stage_bytes);
+  uint8_t* epi_area = smem + (size_t)nst * stage_bytes;   // 1024 B aligned (stage sizes are multiples of 1 KB): epilogue boxes / staging
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_area + kEpiAreaBytes);
   uint64_t* empty_bar = full_bar + nst;
   uint64_t* tmem_full = empty_bar + nst;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;    // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* epi_stage = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tmem_ptr) + 16);  // [kEpiWarps][32][36] f32
+  uint64_t* epi_bar = tmem_empty + 2;      // [kEpiWarps][2]: residual boxes of the TMA epilogue
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(epi_bar + 2 * kEpiWarps);
+  float* epi_stage = reinterpret_cast<float*>(epi_area);  // transposing epilogue: [kEpiWarps][32][36] f32
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform: role loops stay on the uniform datapath
   const int lane = threadIdx.x & 31;
@@ -388,6 +520,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     mbar_init(&tmem_full[1], 1);
     mbar_init(&tmem_empty[0], kEpiWarps);
     mbar_init(&tmem_empty[1], kEpiWarps);
+    for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&epi_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, tmem_cols);
@@ -494,6 +627,12 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     const int ht = (r / p.Wt) % p.Ht;
     const int bt = r / (p.Wt * p.Ht);
     float* stage_buf = epi_stage + (warp - 2) * (32 * kStagePitch);
+    EpiTma et;
+    et.box[0] = smem_u32(epi_area) + (uint32_t)((warp - 2) * 2) * kEpiTmaBufBytes;
+    et.box[1] = et.box[0] + kEpiTmaBufBytes;
+    et.bar[0] = smem_u32(&epi_bar[(warp - 2) * 2]);
+    et.bar[1] = et.bar[0] + 8;
+    et.kb = 0;
     int lt = 0;
     for (int st = cluster_id; st < num_super; st += num_clusters, ++lt) {
       const int mt = (st % m_super) * CM + cm_idx, nt = (st / m_super) * CN + cn_idx;
@@ -506,6 +645,24 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       me.pix = me.ok ? ((size_t)bb * p.H + hh) * (size_t)p.opix_row + (size_t)ww * p.opix_w + p.opix_off : 0;
       me.bb = me.ok ? bb : 0;
       const int buf = lt & 1;
+      if (p.epi_tma) {
+        // TMA epilogue: the tile's rows are contiguous rows of the output matrix, starting at the pixel of tile row 0
+        int eb0, eb1;
+        epi_linear_range(BN, half, eb0, eb1);
+        const int row0 = ((tb * p.Bt) * p.H + th * p.Ht) * p.W + tw * p.Wt + q * 32;
+        if (p.res != nullptr && eb0 < eb1 && lane == 0) {
+          bulk_wait_group_read<1>();   // the first block's box was last read by the store of block kb-2
+          epi_tma_request_res(p, et, et.kb, nt * BN + (eb0 << 5), row0);
+        }
+        mbar_wait(&tmem_full[buf], (lt >> 1) & 1);
+        tc_fence_after();
+        const uint32_t trow_t = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
+        epilogue_tile_tma(p, et, trow_t, nt * BN, eb0, eb1, row0, me.bb, me.ok, lane);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+        continue;
+      }
       // row descriptors + the first block's residual/bias are fetched while the MMAs of this tile still run
       const EpiRows rows = epi_rows(me, p.ldo, lane);
       EpiPrefetch pf0;
@@ -534,6 +691,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   }
 
   if (dbg && threadIdx.x == 0) p.dbg[5] = globaltimer_ns();  // producer done issuing
+  if (p.epi_tma && warp >= 2 && lane == 0) bulk_wait_group_all();   // this thread's TMA stores have been written before the CTA retires
   tc_fence_before();
   __syncthreads();
   if (dbg && threadIdx.x == 0) p.dbg[6] = globaltimer_ns();  // all roles done
@@ -611,12 +769,14 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_pair_kernel(const __grid_co
   const int nst = p.nstages;
   const int b_rows = BN >> 1;                                  // this CTA's half of the B tile
   const uint32_t stage_bytes = kABytes + b_rows * 128;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)nst * stage_bytes);
+  uint8_t* epi_area = smem + (size_t)nst * stage_bytes;   // 1024 B aligned (stage sizes are multiples of 1 KB): epilogue boxes / staging
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_area + kEpiAreaBytes);
   uint64_t* empty_bar = full_bar + nst;
   uint64_t* tmem_full = empty_bar + nst;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;    // [2]  (used in the leader)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* epi_stage = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tmem_ptr) + 16);  // [kEpiWarps][32][36] f32
+  uint64_t* epi_bar = tmem_empty + 2;      // [kEpiWarps][2]: residual boxes of the TMA epilogue
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(epi_bar + 2 * kEpiWarps);
+  float* epi_stage = reinterpret_cast<float*>(epi_area);  // transposing epilogue: [kEpiWarps][32][36] f32
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform: role loops stay on the uniform datapath
   const int lane = threadIdx.x & 31;
@@ -644,6 +804,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_pair_kernel(const __grid_co
     mbar_init(&tmem_full[1], 1);
     mbar_init(&tmem_empty[0], 2 * kEpiWarps);
     mbar_init(&tmem_empty[1], 2 * kEpiWarps);
+    for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&epi_bar[i], 1);
     fence_barrier_init();
   }
   __syncthreads();
@@ -737,6 +898,12 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_pair_kernel(const __grid_co
     const int ht = (r / p.Wt) % p.Ht;
     const int bt = r / (p.Wt * p.Ht);
     float* stage_buf = epi_stage + (warp - 2) * (32 * kStagePitch);
+    EpiTma et;
+    et.box[0] = smem_u32(epi_area) + (uint32_t)((warp - 2) * 2) * kEpiTmaBufBytes;
+    et.box[1] = et.box[0] + kEpiTmaBufBytes;
+    et.bar[0] = smem_u32(&epi_bar[(warp - 2) * 2]);
+    et.bar[1] = et.bar[0] + 8;
+    et.kb = 0;
     int lt = 0;
     for (int pt = pair_id; pt < num_ptiles; pt += num_pairs, ++lt) {
       const int mt = (pt % pm_tiles) * 2 + rank, nt = pt / pm_tiles;
@@ -749,6 +916,27 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_pair_kernel(const __grid_co
       me.pix = me.ok ? ((size_t)bb * p.H + hh) * (size_t)p.opix_row + (size_t)ww * p.opix_w + p.opix_off : 0;
       me.bb = me.ok ? bb : 0;
       const int buf = lt & 1;
+      if (p.epi_tma) {
+        // TMA epilogue: the tile's rows are contiguous rows of the output matrix, starting at the pixel of tile row 0
+        int eb0, eb1;
+        epi_linear_range(BN, half, eb0, eb1);
+        const int row0 = ((tb * p.Bt) * p.H + th * p.Ht) * p.W + tw * p.Wt + q * 32;
+        if (p.res != nullptr && eb0 < eb1 && lane == 0) {
+          bulk_wait_group_read<1>();   // the first block's box was last read by the store of block kb-2
+          epi_tma_request_res(p, et, et.kb, nt * BN + (eb0 << 5), row0);
+        }
+        mbar_wait(&tmem_full[buf], (lt >> 1) & 1);
+        tc_fence_after();
+        const uint32_t trow_t = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
+        epilogue_tile_tma(p, et, trow_t, nt * BN, eb0, eb1, row0, me.bb, me.ok, lane);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (rank == 0) mbar_arrive(&tmem_empty[buf]);
+          else mbar_arrive_remote(mapa_rank(smem_u32(&tmem_empty[buf]), 0));
+        }
+        continue;
+      }
       // row descriptors + the first block's residual/bias are fetched while the MMAs of this tile still run
       const EpiRows rows = epi_rows(me, p.ldo, lane);
       EpiPrefetch pf0;
@@ -779,6 +967,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_pair_kernel(const __grid_co
   }
 
   if (dbg && threadIdx.x == 0) p.dbg[5] = globaltimer_ns();  // producer done issuing
+  if (p.epi_tma && warp >= 2 && lane == 0) bulk_wait_group_all();   // this thread's TMA stores have been written before the CTA retires
   tc_fence_before();
   __syncthreads();
   if (dbg && threadIdx.x == 0) p.dbg[6] = globaltimer_ns();  // all roles done
@@ -810,7 +999,8 @@ static PFN_encodeTiled get_encode() {
 }
 
 static int encode(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                  const uint32_t* box) {
+                  const uint32_t* box, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                  CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   PFN_encodeTiled fn = get_encode();
   if (!fn) return 1001;
   cuuint64_t gd[5];
@@ -822,8 +1012,8 @@ static int encode(CUtensorMap* tm, const void* base, int rank, const uint64_t* d
     es[i] = 1;
     if (i > 0) gs[i - 1] = strides_bytes[i - 1];
   }
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  CUresult r = fn(tm, dtype, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     fprintf(stderr, "sdxl_b200: cuTensorMapEncodeTiled failed (%d) rank=%d dims=[%llu,%llu,%llu,%llu] box=[%u,%u,%u,%u]\n",
@@ -853,6 +1043,16 @@ int make_tmap_rows(CUtensorMap* tm, const __half* base, int rows_per_batch, int 
   uint64_t str[2] = {(uint64_t)pitch * 2, (uint64_t)rows_per_batch * pitch * 2};
   uint32_t box[3] = {64, 128, 1};
   return encode(tm, base, 3, dims, str, box);
+}
+
+// 2-D row-major [rows, ld] view with 32 x 32 boxes for the TMA epilogue (f32: 128-byte box rows, f16: 64-byte box rows)
+static int make_tmap_out(CUtensorMap* tm, const void* base, uint64_t rows, int cols, int ld, bool f32) {
+  const uint64_t es = f32 ? 4 : 2;
+  uint64_t dims[2] = {(uint64_t)cols, rows};
+  uint64_t str[1] = {(uint64_t)ld * es};
+  uint32_t box[2] = {32, 32};
+  return encode(tm, base, 2, dims, str, box, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
 void igemm_pick_box(int W, int H, int* Wt, int* Ht, int* Bt) {
@@ -932,7 +1132,7 @@ static int device_sms() {
 }
 
 static size_t igemm_smem_bytes(int nst, int b_rows) {
-  return (size_t)nst * (kABytes + b_rows * 128) + 1024 /*align slack*/ + (2 * nst + 4) * 8 + 32 + kEpiStageBytes;
+  return (size_t)nst * (kABytes + b_rows * 128) + 1024 /*align slack*/ + (2 * nst + 4 + 2 * kEpiWarps) * 8 + 32 + kEpiAreaBytes;
 }
 
 int igemm_configure(IgemmParams& p, const IgemmOperands& o, int outW, int outH, int outB, int mode, int geglu_bn) {
@@ -989,10 +1189,27 @@ int igemm_configure(IgemmParams& p, const IgemmOperands& o, int outW, int outH, 
   if (!r) r = make_tmap_wgt(&p.tmB, o.w, o.N, o.Ktot, p.BN / CM);
   if (r) return r;
   const int stage_bytes = kABytes + (p.pair ? p.BN * 64 : p.BN * 128);
-  int nst = (226 * 1024 - 1024 - 256 - kEpiStageBytes) / stage_bytes;
+  int nst = (226 * 1024 - 1024 - 512 - kEpiAreaBytes) / stage_bytes;
   if (nst > 8) nst = 8;
   if (nst < 2) nst = 2;
   p.nstages = nst;
+  // TMA epilogue: LINEAR tiles, 32-column blocks, tile rows = contiguous output rows (full image rows per tile and either whole
+  // images or a single image per tile), f32 output (+ optional f32 residual of the same leading dimension) or f16 output without
+  // residual. SDXL_B200_EPI_TMA=0 keeps the transposing epilogue everywhere (A/B).
+  static const bool tma_on = !(getenv("SDXL_B200_EPI_TMA") && getenv("SDXL_B200_EPI_TMA")[0] == '0');
+  p.epi_tma = 0;
+  const bool contiguous = (p.Ht == 1 && p.Bt == 1) ||   // a tile is a run of pixels inside one image row (token GEMMs: H = 1, W = M)
+                          (p.Wt == outW && (p.Ht == outH || p.Bt == 1) && outH % p.Ht == 0);   // or whole image rows
+  const bool dtype_ok = p.out_f32 ? (p.res == nullptr || p.ldr == p.ldo) : (p.res == nullptr);
+  if (tma_on && mode == IGEMM_LINEAR && contiguous && dtype_ok && p.out != nullptr && (o.N % 32) == 0 && (p.BN % 32) == 0 && (o.N % p.BN) == 0 &&
+      p.ldo >= o.N && ((size_t)p.ldo * (p.out_f32 ? 4 : 2)) % 16 == 0 && ((uintptr_t)p.out % 16) == 0 && ((uintptr_t)p.res % 16) == 0) {
+    const uint64_t rows = (uint64_t)outB * outH * outW;
+    int r2 = make_tmap_out(&p.tmOut, p.out, rows, o.N, p.ldo, p.out_f32 != 0);
+    if (!r2 && p.res) r2 = make_tmap_out(&p.tmRes, p.res, rows, o.N, p.ldr, true);
+    if (!r2 && !p.res) p.tmRes = p.tmOut;
+    if (r2) return r2;
+    p.epi_tma = 1;
+  }
   return 0;
 }
 
@@ -1001,6 +1218,7 @@ int igemm_launch(cudaStream_t st, IgemmParams& p) {
   if (p.res != nullptr && p.ldr != p.ldo) return 1003;
   if ((unsigned long long)p.Bn * p.H * (unsigned long long)p.opix_row * (unsigned long long)p.ldo >= (1ull << 32)) return 1004;
   const size_t smem = igemm_smem_bytes(p.nstages, p.pair ? p.BN / 2 : p.BN);
+  if (p.epi_tma && (p.opix_w != 1 || p.opix_off != 0 || p.opix_row != p.W)) p.epi_tma = 0;   // re-mapped output pixels (phase-decomposed upsample conv)
   IgemmDev* D = igemm_dev();
   if (!D) return 1009;
   if (!D->attr) {

@@ -108,6 +108,10 @@ struct alignas(64) IgemmParams {
   // upsample + 3x3 conv is run as four 2x2 convolutions on the original image, each writing one (row, column) parity of the
   // upsampled output: opix_row = 4W, opix_w = 2, opix_off = a*2W + b.
   int opix_row, opix_w, opix_off;
+  // TMA epilogue (igemm.cu "epilogue through TMA"): set by igemm_configure when the tile's 128 rows are contiguous rows of a plain
+  // [pixels, ldo] output (N and BN multiples of 32, LINEAR mode); igemm_launch drops it if the caller re-mapped the output pixels.
+  CUtensorMap tmOut, tmRes;   // 2-D [pixels, ldo] views, box 32 rows x 32 columns (f32: SWIZZLE_128B, f16: SWIZZLE_64B)
+  int epi_tma;
   // host-computed reciprocals (floor(2^32/d)+1; q = umulhi(n, m), exact while n*d < 2^32; 0 = use '/') for the tile-index
   // divisions of the producer warp: on the critical path between griddepcontrol.wait and the first TMA issue
   unsigned fd_pm, fd_w, fd_h, fd_wh;   // divisors: pair M tiles (or M tiles), tilesW, tilesH, tilesW*tilesH

@@ -38,6 +38,7 @@ def sample(embedder, diffuser, decoder, prompt: str, guidance: float = 7.5, n_st
     if reference_rgb is not None:
         ref_latent = decoder.image_to_latent(reference_rgb)                              # main.rs:158
         lh, lw = int(ref_latent.shape[2]), int(ref_latent.shape[3])
+        cond.resolution = (8 * lh, 8 * lw)   # the sampler's latent extent follows the encoded reference (== the image size for the x8 SDXL VAE)
         mask = make_inpaint_mask(resolution, (lh, lw), *crop, crop_out=crop_out)
         latent = diffuser.sample_latent_with_inpainting(cond, guidance, n_steps, ref_latent, mask, init_noise=noise, seed=seed)   # main.rs:246
     else:
