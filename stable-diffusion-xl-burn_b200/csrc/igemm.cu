@@ -391,6 +391,49 @@ __device__ __forceinline__ void epilogue_tile_tma(const IgemmParams& p, EpiTma& 
   }
 }
 
+// GEGLU tile through TMA stores: value columns [0, BN/2) and gate columns [BN/2, BN) of the accumulator -> BN/2 f16 outputs
+// (reference unet/mod.rs:942-956), 32 output columns per box (32 rows x 64 B, SWIZZLE_64B). No residual, bias on both halves.
+__device__ __forceinline__ void epilogue_tile_tma_geglu(const IgemmParams& p, EpiTma& e, uint32_t trow, int nt, int n0, int half, int row0,
+                                                        int lane) {
+  const int hb = p.BN >> 1;
+  const int nb = hb >> 5;
+  const int b0 = half == 0 ? 0 : ((nb + 1) >> 1), b1 = half == 0 ? ((nb + 1) >> 1) : nb;
+  for (int bI = b0; bI < b1; ++bI) {
+    const int c = bI << 5;
+    const uint32_t cur = e.kb & 1u;
+    if (lane == 0) bulk_wait_group_read<1>();   // this block's box: last read by the store of block kb-2
+    uint32_t v[32], g[32];
+    tmem_ld32(trow + c, v);
+    tmem_ld32(trow + hb + c, g);
+    tmem_ld_wait();
+    __syncwarp();
+    const uint32_t rowa = e.box[cur] + (uint32_t)lane * 64u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t h[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int k = 8 * j + 2 * i;
+        float x0 = __uint_as_float(v[k]), x1 = __uint_as_float(v[k + 1]), y0 = __uint_as_float(g[k]), y1 = __uint_as_float(g[k + 1]);
+        if (p.bias != nullptr) {
+          x0 += __ldg(p.bias + n0 + c + k); x1 += __ldg(p.bias + n0 + c + k + 1);
+          y0 += __ldg(p.bias + n0 + hb + c + k); y1 += __ldg(p.bias + n0 + hb + c + k + 1);
+        }
+        __half2 t = __floats2half2_rn(x0 * gelu_erf_f(y0), x1 * gelu_erf_f(y1));
+        h[i] = *reinterpret_cast<uint32_t*>(&t);
+      }
+      sts128u(rowa + ((uint32_t)(j ^ ((lane >> 1) & 3)) << 4), make_uint4(h[0], h[1], h[2], h[3]));
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(&p.tmOut, e.box[cur], nt * hb + c, row0);
+      bulk_commit_group();
+    }
+    ++e.kb;
+  }
+}
+
 // phase-2 row descriptors from the per-lane (lane = row) description
 __device__ __forceinline__ EpiRows epi_rows(const EpiRow& me, int ld, int lane) {
   EpiRows r;
@@ -657,7 +700,8 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         mbar_wait(&tmem_full[buf], (lt >> 1) & 1);
         tc_fence_after();
         const uint32_t trow_t = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
-        epilogue_tile_tma(p, et, trow_t, nt * BN, eb0, eb1, row0, me.bb, me.ok, lane);
+        if (p.mode == IGEMM_GEGLU) epilogue_tile_tma_geglu(p, et, trow_t, nt, nt * BN, half, row0, lane);
+        else epilogue_tile_tma(p, et, trow_t, nt * BN, eb0, eb1, row0, me.bb, me.ok, lane);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[buf]);
@@ -928,7 +972,8 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_pair_kernel(const __grid_co
         mbar_wait(&tmem_full[buf], (lt >> 1) & 1);
         tc_fence_after();
         const uint32_t trow_t = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
-        epilogue_tile_tma(p, et, trow_t, nt * BN, eb0, eb1, row0, me.bb, me.ok, lane);
+        if (p.mode == IGEMM_GEGLU) epilogue_tile_tma_geglu(p, et, trow_t, nt, nt * BN, half, row0, lane);
+        else epilogue_tile_tma(p, et, trow_t, nt * BN, eb0, eb1, row0, me.bb, me.ok, lane);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -1208,6 +1253,14 @@ int igemm_configure(IgemmParams& p, const IgemmOperands& o, int outW, int outH, 
     if (!r2 && p.res) r2 = make_tmap_out(&p.tmRes, p.res, rows, o.N, p.ldr, true);
     if (!r2 && !p.res) p.tmRes = p.tmOut;
     if (r2) return r2;
+    p.epi_tma = 1;
+  }
+  // GEGLU tiles: [pixels, N/2] f16 output, 32-column boxes
+  if (tma_on && mode == IGEMM_GEGLU && contiguous && !p.out_f32 && p.res == nullptr && p.out != nullptr && (p.BN % 64) == 0 && (o.N % p.BN) == 0 &&
+      p.ldo >= o.N / 2 && ((size_t)p.ldo * 2) % 16 == 0 && ((uintptr_t)p.out % 16) == 0 && p.bias_bstride == 0) {
+    int r2 = make_tmap_out(&p.tmOut, p.out, (uint64_t)outB * outH * outW, o.N / 2, p.ldo, false);
+    if (r2) return r2;
+    p.tmRes = p.tmOut;
     p.epi_tma = 1;
   }
   return 0;
