@@ -240,11 +240,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
     int kvc = 0, item = 0;
     int dn = 0;
     const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && lane == 0;
-    // Issue order (one in-order tensor pipe, two slots): slot B runs HALF A PERIOD behind slot A, so one slot's exp phase
-    // (the XU-bound part) covers the other slot's hand-over + MMA latency. The stagger is created once per item — S_B(0) is
-    // issued only when slot A hands over its first P — and is self-sustaining afterwards. Per hand-over of slot X at block j:
-    // S_X(j+1) = Q_X K_{j+1}^T goes FIRST (it is what the softmax warps wait for; S_X(j) is dead once P_X(j) exists), then
-    // O_X += P_X(j) V_j.
+    // Issue order (one in-order tensor pipe, two slots): per hand-over of slot X at block j, S_X(j+1) = Q_X K_{j+1}^T goes FIRST
+    // (it is what the softmax warps wait for; S_X(j) is dead once P_X(j) exists), then O_X += P_X(j) V_j. Starting slot B half a
+    // period behind slot A was measured and makes no difference (any offset between the slots is neutrally stable).
     for (int tile = t_begin; tile < t_end; ++item) {
       const int qt = tile % nqt;
       const bool hasB = (qt + 1 < nqt) && (tile + 1 < t_end);
@@ -259,6 +257,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
       if (hasB) {
         mbar_wait(&q_full[qs0 + 1], (qf_ph >> (qs0 + 1)) & 1u);
         qf_ph ^= 1u << (qs0 + 1);
+        tc_fence_after();
+        mma_qk_commit(tmem_base + kColS + 128, q_lo0 + (qs0 + 1) * kTile16, k_lo0 + st * kTile16, dhi, idesc_qk, &s_full[1]);
       }
       for (int j = 0; j < nblk; ++j, ++kvc) {
         const bool more = j + 1 < nblk;
@@ -269,8 +269,6 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         pf_ph ^= 1u;
         if (dbg && dn < 256) p.dbg[2048 + dn * 4 + 0] = clock64();
         tc_fence_after();
-        if (j == 0 && hasB)   // start of slot B, half a period behind A
-          mma_qk_commit(tmem_base + kColS + 128, q_lo0 + (qs0 + 1) * kTile16, k_lo0 + st * kTile16, dhi, idesc_qk, &s_full[1]);
         if (more) {
           mbar_wait(&kv_full[stn], ((kvc + 1) / kKvStages) & 1);
           tc_fence_after();

@@ -39,8 +39,8 @@ def main():
             qf, kf, vf = (t.float().reshape(B, -1, nh, 64).transpose(1, 2) for t in (qs[0], ks[0], vs[0]))
             ref = torch.nn.functional.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2).reshape(B, T, C)
             err = float((out.float() - ref).norm() / ref.norm())
-            for i in range(3):
-                ctx.qkv_attention(qs[i], ks[i], vs[i], None, nh)
+            for i in range(24):
+                ctx.qkv_attention(qs[i % 4], ks[i % 4], vs[i % 4], None, nh)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             n = 20
