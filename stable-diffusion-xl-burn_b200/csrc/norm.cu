@@ -160,14 +160,13 @@ __global__ void gn_apply_kernel(const float* __restrict__ x1, int C1, const floa
   const int b = blockIdx.y;
   const int cpg = C / n_group;
   const int c = v * 8;
-  float sc[8], sh[8], mu[8];   // y = (x - mean) * (rstd * gamma) + beta: centre first (exact in f32 when x is near the mean)
+  float sc[8], sh[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int g = (c + i) / cpg;
     const float mean = final_stats[((size_t)b * n_group + g) * 2], rstd = final_stats[((size_t)b * n_group + g) * 2 + 1];
     sc[i] = rstd * gamma[c + i];
-    sh[i] = beta[c + i];
-    mu[i] = mean;
+    sh[i] = fmaf(-mean, sc[i], beta[c + i]);   // y = x * sc + sh: the cancellation costs |mean| / sigma * 2^-24 absolute, far below f16
   }
   const float* src;
   int cc, Cs;
@@ -190,7 +189,7 @@ __global__ void gn_apply_kernel(const float* __restrict__ x1, int C1, const floa
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      float t = fmaf(f[i] - mu[i], sc[i], sh[i]);
+      float t = fmaf(f[i], sc[i], sh[i]);
       if (silu) t = silu_f(t);
       f[i] = t;
     }
