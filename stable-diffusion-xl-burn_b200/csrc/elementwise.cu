@@ -111,52 +111,70 @@ int timestep_embedding_launch(cudaStream_t st, const int* t_dev, int nt, int dim
 // First conv (4 -> model_channels, 3x3 pad 1; reference unet/mod.rs:116-120). K = 36: CUDA cores.
 // x: NCHW (f16 or f32) [Bx, Cin, H, W]; output batch b reads image (b % Bx). y: NHWC f32.
 // ------------------------------------------------------------------------------------------------
+// One thread = 4 output channels x 8 consecutive pixels of a row: every weight float4 read from shared memory feeds 32 FMAs
+// (at one pixel per thread the kernel was bound by the LDS.128 per 4 FMAs: 158 us for the UNet's 2x128x128x320 output).
+constexpr int kConvInPix = 8;
 template <typename TIn>
-__global__ void conv_in_kernel(const TIn* __restrict__ x, int Bx, int B, int Cin, int H, int W,
-                               const float* __restrict__ w, const float* __restrict__ bias, int Cout,
-                               float* __restrict__ y) {
+__global__ void __launch_bounds__(256) conv_in_kernel(const TIn* __restrict__ x, int Bx, int B, int Cin, int H, int W,
+                                                      const float* __restrict__ w, const float* __restrict__ bias, int Cout,
+                                                      float* __restrict__ y) {
   extern __shared__ float sw[];  // [9*Cin][Cout]  (k-major: lanes = consecutive output channels, conflict-free)
   const int kk = 9 * Cin;
-  for (int i = threadIdx.x; i < Cout * kk; i += blockDim.x) {
-    const int co = i / kk, k = i % kk;
-    sw[k * Cout + co] = w[i];
-  }
+  for (int co = threadIdx.x; co < Cout; co += blockDim.x)          // lanes = consecutive rows of w: conflict-free smem writes,
+    for (int k = 0; k < kk; ++k) sw[k * Cout + co] = w[co * kk + k];   // the rows' lines stay in L1 across the k loop
   __syncthreads();
   const int cvec = Cout / 4;
-  const long total = (long)B * H * W * cvec;
+  const int nseg = (W + kConvInPix - 1) / kConvInPix;
+  const long total = (long)B * H * nseg * cvec;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
     const int cv = (int)(idx % cvec);
-    const long pix = idx / cvec;
-    const int ww = (int)(pix % W);
-    const int hh = (int)((pix / W) % H);
-    const int b = (int)(pix / ((long)W * H));
+    const long seg = idx / cvec;
+    const int w0 = (int)(seg % nseg) * kConvInPix;
+    const int hh = (int)((seg / nseg) % H);
+    const int b = (int)(seg / ((long)nseg * H));
     const TIn* xb = x + (size_t)(b % Bx) * Cin * H * W;
-    float4 acc = bias ? *reinterpret_cast<const float4*>(bias + cv * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 b4 = bias ? *reinterpret_cast<const float4*>(bias + cv * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 acc[kConvInPix];
+#pragma unroll
+    for (int i = 0; i < kConvInPix; ++i) acc[i] = b4;
     for (int kh = 0; kh < 3; ++kh) {
       const int ih = hh + kh - 1;
       if (ih < 0 || ih >= H) continue;
-      for (int kw = 0; kw < 3; ++kw) {
-        const int iw = ww + kw - 1;
-        if (iw < 0 || iw >= W) continue;
-        for (int c = 0; c < Cin; ++c) {
-          const float v = (float)xb[((size_t)c * H + ih) * W + iw];   // broadcast across the warp's channel lanes
+      for (int c = 0; c < Cin; ++c) {
+        const TIn* xr = xb + ((size_t)c * H + ih) * W;
+        float xv[kConvInPix + 2];                                  // the row segment with its halo; same address in all lanes
+#pragma unroll
+        for (int i = 0; i < kConvInPix + 2; ++i) {
+          const int iw = w0 + i - 1;
+          xv[i] = (iw >= 0 && iw < W) ? (float)xr[iw] : 0.f;
+        }
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
           const float4 wv = *reinterpret_cast<const float4*>(sw + ((kh * 3 + kw) * Cin + c) * Cout + cv * 4);
-          acc.x = fmaf(v, wv.x, acc.x); acc.y = fmaf(v, wv.y, acc.y); acc.z = fmaf(v, wv.z, acc.z); acc.w = fmaf(v, wv.w, acc.w);
+#pragma unroll
+          for (int i = 0; i < kConvInPix; ++i) {
+            const float v = xv[i + kw];
+            acc[i].x = fmaf(v, wv.x, acc[i].x); acc[i].y = fmaf(v, wv.y, acc[i].y);
+            acc[i].z = fmaf(v, wv.z, acc[i].z); acc[i].w = fmaf(v, wv.w, acc[i].w);
+          }
         }
       }
     }
-    *reinterpret_cast<float4*>(y + pix * Cout + cv * 4) = acc;
+    float* yo = y + (((size_t)b * H + hh) * W + w0) * Cout + cv * 4;
+#pragma unroll
+    for (int i = 0; i < kConvInPix; ++i)
+      if (w0 + i < W) *reinterpret_cast<float4*>(yo + (size_t)i * Cout) = acc[i];
   }
 }
 int conv_in_launch_t(cudaStream_t st, const void* x, int x_f32, int Bx, int B, int Cin, int H, int W, const float* w,
                      const float* bias, int Cout, float* y) {
   if (Cin > 8 || (Cout & 3)) return 2002;
   const size_t smem = (size_t)Cout * 9 * Cin * sizeof(float);
-  if (smem > 48 * 1024) {
-    cudaFuncSetAttribute(conv_in_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(conv_in_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  }
-  const long total = (long)B * H * W * (Cout / 4);
+  static bool done_f[64], done_h[64];
+  if (smem > 200 * 1024) return 2002;
+  if (int r = smem_optin(conv_in_kernel<float>, 200 * 1024, done_f)) return r;
+  if (int r = smem_optin(conv_in_kernel<__half>, 200 * 1024, done_h)) return r;
+  const long total = (long)B * H * ((W + kConvInPix - 1) / kConvInPix) * (Cout / 4);
   int grid = cdiv(total, 256);
   if (grid > 148 * 4) grid = 148 * 4;
   if (x_f32)

@@ -56,7 +56,7 @@ def tiny_refiner(ctx):
     d.close()
 
 
-@pytest.mark.parametrize("B,h,w,n_ctx,t", [(1, 8, 8, 3, 1), (2, 16, 16, 77, 999), (1, 32, 32, 77, 500), (3, 8, 16, 5, 249)])
+@pytest.mark.parametrize("B,h,w,n_ctx,t", [(1, 8, 8, 3, 1), (2, 16, 16, 77, 999), (1, 32, 32, 77, 500), (3, 8, 16, 5, 249), (1, 12, 20, 7, 700)])   # last: a row that is not a multiple of the first conv's 8-pixel segments
 def test_unet_forward_vs_oracle(tiny, B, h, w, n_ctx, t):
     d, wf = tiny
     x = arb(B, 4, h, w)
