@@ -30,26 +30,39 @@ __global__ void gemv_kernel(const float* __restrict__ in, int in_bstride, int Bv
 #pragma unroll
   for (int b = 0; b < MAXB; ++b) acc[b] = 0.f;
   const __half* w = W + (size_t)n * ldw;
-  if ((K & 7) == 0 && (ldw & 7) == 0) {
-    for (int k0 = lane * 8; k0 < K; k0 += 256) {
-      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(w + k0));
-      const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
-      float wf[8];
+  if ((K & 7) == 0 && (ldw & 7) == 0 && (in_bstride & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+    // four 16-byte weight loads in flight per lane before the first FMA (a K = 1280 row is 5 loads per lane: one DRAM round
+    // trip each if issued one per iteration), activations as float4 (L1 hits)
+    for (int k0 = lane * 8; k0 < K; k0 += 1024) {
+      uint4 raw[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = __half22float2(h2[i]);
-        wf[2 * i] = f.x;
-        wf[2 * i + 1] = f.y;
-      }
+      for (int u = 0; u < 4; ++u)
+        raw[u] = (k0 + u * 256 < K) ? __ldg(reinterpret_cast<const uint4*>(w + k0 + u * 256)) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-      for (int b = 0; b < MAXB; ++b) {
-        if (b < Bv) {
-          const float* x = in + (size_t)b * in_bstride + k0;
+      for (int u = 0; u < 4; ++u) {
+        const int kk = k0 + u * 256;
+        if (kk < K) {
+          const __half2* h2 = reinterpret_cast<const __half2*>(&raw[u]);
+          float wf[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float v = x[i];
-            if (in_silu) v = silu_f(v);
-            acc[b] = fmaf(v, wf[i], acc[b]);
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(h2[i]);
+            wf[2 * i] = f.x;
+            wf[2 * i + 1] = f.y;
+          }
+#pragma unroll
+          for (int b = 0; b < MAXB; ++b) {
+            if (b < Bv) {
+              const float4* x4 = reinterpret_cast<const float4*>(in + (size_t)b * in_bstride + kk);
+              const float4 xa = __ldg(x4), xb = __ldg(x4 + 1);
+              float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float v = xv[i];
+                if (in_silu) v = silu_f(v);
+                acc[b] = fmaf(v, wf[i], acc[b]);
+              }
+            }
           }
         }
       }
@@ -84,8 +97,12 @@ int gemv_launch(cudaStream_t st, const float* in, int in_bstride, int Bv, int K,
                 const float* add, int add_bstride, int N, int in_silu, int out_silu, float* out, int out_bstride) {
   if (Bv > 8) return 2001;
   const int warps = 8;
-  gemv_kernel<8><<<cdiv(N, warps), warps * 32, 0, st>>>(in, in_bstride, Bv, K, W, ldw, bias, add, add_bstride, N, in_silu,
-                                                         out_silu, out, out_bstride);
+  if (Bv <= 2)
+    gemv_kernel<2><<<cdiv(N, warps), warps * 32, 0, st>>>(in, in_bstride, Bv, K, W, ldw, bias, add, add_bstride, N, in_silu,
+                                                           out_silu, out, out_bstride);
+  else
+    gemv_kernel<8><<<cdiv(N, warps), warps * 32, 0, st>>>(in, in_bstride, Bv, K, W, ldw, bias, add, add_bstride, N, in_silu,
+                                                           out_silu, out, out_bstride);
   return (int)cudaGetLastError();
 }
 

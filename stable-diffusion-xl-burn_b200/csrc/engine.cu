@@ -522,15 +522,17 @@ struct UNetPlanBuilder : PlanBuilder {
       // x = x + mlp(norm3(x))
       ln(s_tok, b.n3, M, s_a16);
       linear(s_a16, M, b.ff1, IGEMM_GEGLU, s_ff, 0, 4 * C, nullptr, 0);
-      linear(s_ff, M, b.ff2, IGEMM_LINEAR, s_tok, 1, C, s_tok, C);
+      // the last block's stream only feeds proj_out: its residual add writes the f16 operand directly (no f32 copy, no cast launch)
+      if (&b == &s.blocks.back()) linear(s_ff, M, b.ff2, IGEMM_LINEAR, s_a16, 0, C, s_tok, C);
+      else linear(s_ff, M, b.ff2, IGEMM_LINEAR, s_tok, 1, C, s_tok, C);
     }
-    // proj_out(tokens) + x_in  (f32 stream -> f16 operand)
-    if (!err) {
+    if (s.blocks.empty() && !err) {   // no block to fold the cast into
       Op op{};
       op.kind = OP_CAST16;
       op.cs = {s_tok, (size_t)M * C, s_a16};
       P->ops.push_back(op);
     }
+    // proj_out(tokens) + x_in
     linear(s_a16, M, s.proj_out, IGEMM_LINEAR, out, 1, C, x, C);
     return out;
   }

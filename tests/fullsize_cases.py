@@ -72,3 +72,22 @@ def inpaint_inputs():
     init = _randn(300, 1, 4, 128, 128)
     step_noise = torch.stack([_randn(301 + i, 1, 4, 128, 128) for i in range(INPAINT["n_steps"])])
     return ref, mask, init, step_noise
+
+
+# ---- latent decoder / encoder at 1024^2: one decode and one encode vs the f32 oracle ----
+VAE_WEIGHT_SEED = 7
+
+
+def vae_1024_inputs(scale_factor: float):
+    """(latent [1,4,128,128] scaled like a sampler output, u8 RGB image [1,1024,1024,3])"""
+    lat = _randn(301, 1, 4, 128, 128) * scale_factor
+    rgb = torch.randint(0, 256, (1, 1024, 1024, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(302))
+    return lat, rgb
+
+
+def vae_image_digest(img: torch.Tensor):
+    """The 12 MB f32 image is committed as two 196 KB digests that together see every pixel: 8x8 block means
+    (all pixels, averaged) and one raw pixel per block (no averaging)."""
+    pool = torch.nn.functional.avg_pool2d(img.double(), 8).float()
+    samp = img[:, :, 3::8, 5::8].contiguous()
+    return pool, samp

@@ -12,6 +12,8 @@ hour on 8 cores. The outputs are the fixtures tests/test_fullsize_parity_gpu.py 
     base_config2.npz       BASELINE config 2: 1024^2, n = 30 (31 iterations), cfg 7.5 (final latent + checkpoints)
     refiner_10step.npz     refine_latent(step_start 800, n 50) = 10 refiner iterations at 1024^2
     base_inpaint10.npz     10-iteration inpainting run at 1024^2 (mask = top 25 latent rows), cfg 7.5
+    vae_1024.npz           LatentDecoder::decode_latent of a 128x128 latent (digests of the 1024^2 image, fullsize_cases.vae_image_digest)
+                           and LatentDecoder::image_to_latent of a 1024^2 u8 image (full latent)
 
 PARITY UNPINNED: these come from the restated oracle, not from the reference binary (which cannot be built here,
 see DESIGN.md); they pin the CUDA path to the oracle at BASELINE.json's own sizes.
@@ -44,7 +46,7 @@ def log(msg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--threads", type=int, default=os.cpu_count())
-    ap.add_argument("--only", default="fwd,config1,config2,refiner,inpaint")
+    ap.add_argument("--only", default="fwd,config1,config2,refiner,inpaint,vae")
     args = ap.parse_args()
     torch.set_num_threads(args.threads)
     only = set(args.only.split(","))
@@ -111,6 +113,20 @@ def main():
             out = O.refine_latent(cfg, w, alphas, lat, O.OracleConditioning(**cond), c["guidance"], c["step_start"], c["n_steps"], noise)
             log(f"refiner 10 iterations: {time.time() - t0:.0f} s")
             np.savez(os.path.join(HERE, "refiner_10step.npz"), out=out.numpy())
+        if "vae" in only:
+            from oracle import vae_oracle as VO
+            cfg = sdxl_b200.SDXL_VAE
+            w = O.to_f32(sdxl_b200.synth_weights(cfg, seed=FC.VAE_WEIGHT_SEED, device="cpu"))
+            lat, rgb = FC.vae_1024_inputs(cfg.scale_factor)
+            t0 = time.time()
+            img = VO.decode_latent(cfg, w, lat)
+            log(f"VAE decode 1024^2: {time.time() - t0:.0f} s")
+            pool, samp = FC.vae_image_digest(img)
+            t0 = time.time()
+            enc = VO.image_to_latent(cfg, w, rgb)
+            log(f"VAE encode 1024^2: {time.time() - t0:.0f} s")
+            np.savez(os.path.join(HERE, "vae_1024.npz"), pool=pool.numpy(), samp=samp.numpy(), norm=float(img.double().norm()),
+                     latent=enc.numpy())
     log(f"done in {time.time() - t_all:.0f} s")
 
 

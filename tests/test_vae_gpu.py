@@ -118,6 +118,27 @@ def test_sdxl_vae_1024_properties(full):
     assert torch.equal(b[0], a[0]) and torch.equal(b[1], a[0])
 
 
+def test_sdxl_vae_1024_vs_golden(full):
+    """Full size against the CPU f32 oracle (committed digests, tests/golden/make_fullsize_golden.py --only vae): the decoded 1024^2
+    image through its 8x8 block means (every pixel contributes) and one raw pixel per block; the encoded latent in full."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import fullsize_cases as FC
+    d, _ = full
+    g = np.load(os.path.join(GOLD, "vae_1024.npz"))
+    lat, rgb = FC.vae_1024_inputs(SDXL_VAE.scale_factor)
+    img = d.decode_latent(lat.cuda()).cpu()
+    pool, samp = FC.vae_image_digest(img)
+    e_pool, e_samp = rel_err(pool, torch.from_numpy(g["pool"])), rel_err(samp, torch.from_numpy(g["samp"]))
+    e_norm = abs(float(img.double().norm()) / float(g["norm"]) - 1.0)
+    print(f"SDXL VAE 1024^2 decode vs oracle: block means rel err {e_pool:.2e}, raw samples rel err {e_samp:.2e}, |image| rel {e_norm:.1e}")
+    assert e_pool <= TOL and e_samp <= TOL and e_norm <= 1e-3
+    enc = d.image_to_latent(rgb.cuda()).cpu()
+    e_enc = rel_err(enc, torch.from_numpy(g["latent"]))
+    print(f"SDXL VAE 1024^2 image_to_latent vs oracle: rel err {e_enc:.2e}")
+    assert enc.shape == (1, 4, 128, 128) and e_enc <= TOL
+
+
 # ---- encoder half (LatentDecoder::{encode_image, image_to_latent}) ---------------------------------------------------
 def test_encode_golden_fixture(tiny):
     d, _ = tiny
