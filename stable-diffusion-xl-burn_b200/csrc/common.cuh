@@ -43,7 +43,7 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
 }
 __device__ __forceinline__ uint64_t globaltimer_ns() {
   uint64_t t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)::"memory");   // "memory": not to be moved across barriers (timeline stamps)
   return t;
 }
 

@@ -1284,6 +1284,61 @@ extern "C" int sdxl_dbg_attention_timeline(sdxl_ctx* c, int B, int T, int S, int
 // Diagnostics: in-kernel timeline (%globaltimer, ns) of CTA 0 of one igemm launch on a synthetic [M,K]x[K,N] problem.
 // stamps_host[0..6] = prologue done, dependencies resolved, first operands landed, first accumulator complete,
 // first epilogue done, producer done, all roles done; stamps_host[7] = CUDA-event duration of the launch in ns.
+// Launch ramp / drain of back-to-back launches of one GEMM (programmatic dependent launch, eager): every CTA stamps its entry, the end of
+// its prologue, the moment its dependencies are resolved and its exit. out_host: n_launch x 8 = {first, last} x {entry, prologue done,
+// dependencies resolved, exit} in ns relative to the first entry of launch 0; out_host[n_launch * 8] = grid size.
+extern "C" int sdxl_dbg_igemm_gaps(sdxl_ctx* c, int M, int K, int N, int with_residual, int n_launch, int64_t* out_host) {
+  if (!c || !out_host || n_launch < 1 || n_launch > 16) return -1;
+  TmpBufs T(c->stream);
+  const int Kpad = (K + 63) / 64 * 64;
+  __half* x = (__half*)T.get((size_t)M * K * 2);
+  __half* w = (__half*)T.get((size_t)N * Kpad * 2);
+  float* bias = (float*)T.get((size_t)N * 4);
+  float* res = (float*)T.get((size_t)M * N * 4);
+  void* out = T.get((size_t)M * N * 4);
+  const size_t per = 256 * 8;   // stamps per launch (grid <= 256 CTAs)
+  unsigned long long* dbg = (unsigned long long*)T.get((size_t)n_launch * per * 8);
+  if (!x || !w || !bias || !res || !out || !dbg) return fail(c, 5400, "temporary allocation failed");
+  CU(c, cudaMemsetAsync(x, 0, (size_t)M * K * 2, c->stream));
+  CU(c, cudaMemsetAsync(w, 0, (size_t)N * Kpad * 2, c->stream));
+  CU(c, cudaMemsetAsync(bias, 0, (size_t)N * 4, c->stream));
+  CU(c, cudaMemsetAsync(res, 0, (size_t)M * N * 4, c->stream));
+  CU(c, cudaMemsetAsync(dbg, 0, (size_t)n_launch * per * 8, c->stream));
+  IgemmParams p{};
+  p.nseg = 1;
+  p.seg[0] = {0, 0, 0, 0, Kpad / 64};
+  p.out = out; p.out_f32 = 1; p.ldo = N;
+  p.bias = bias; p.bias_bstride = 0;
+  p.res = with_residual ? res : nullptr; p.ldr = N;
+  IgemmOperands o{x, 1, 1, M, K, K, nullptr, 0, 0, 0, 0, 0, w, N, Kpad};
+  int r = igemm_configure(p, o, M, 1, 1, IGEMM_LINEAR, 0);
+  if (r) return fail(c, r, "igemm configuration failed");
+  if (!p.pair) return fail(c, 5401, "sdxl_dbg_igemm_gaps: shape does not use the 2-CTA kernel");
+  for (int i = 0; i < 3; ++i) KL(c, igemm_launch(c->stream, p));
+  for (int i = 0; i < n_launch; ++i) {
+    p.dbg_all = dbg + (size_t)i * per;
+    KL(c, igemm_launch(c->stream, p));
+  }
+  std::vector<unsigned long long> h((size_t)n_launch * per);
+  CU(c, cudaMemcpyAsync(h.data(), dbg, h.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  int grid = 0;
+  while (grid < 256 && h[(size_t)grid * 8] != 0) ++grid;
+  const unsigned long long t0 = [&] { unsigned long long m = ~0ull; for (int b = 0; b < grid; ++b) m = std::min(m, h[(size_t)b * 8]); return m; }();
+  for (int i = 0; i < n_launch; ++i)
+    for (int k = 0; k < 8; ++k) {
+      unsigned long long lo = ~0ull, hi = 0;
+      for (int b = 0; b < grid; ++b) {
+        const unsigned long long v = h[(size_t)i * per + (size_t)b * 8 + k];
+        lo = std::min(lo, v); hi = std::max(hi, v);
+      }
+      out_host[i * 16 + 2 * k] = (int64_t)(lo - t0);
+      out_host[i * 16 + 2 * k + 1] = (int64_t)(hi - t0);
+    }
+  out_host[n_launch * 16] = grid;
+  return 0;
+}
+
 extern "C" int sdxl_dbg_igemm_timeline(sdxl_ctx* c, int M, int K, int N, int geglu, int with_residual, uint64_t* stamps_host) {
   if (!c || !stamps_host) return -1;
   TmpBufs T(c->stream);

@@ -551,20 +551,18 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   uint32_t tmem_cols = 32;
   while (tmem_cols < (uint32_t)(2 * BN)) tmem_cols <<= 1;
 
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.tmA0);
-    tma_prefetch_desc(&p.tmA1);
-    tma_prefetch_desc(&p.tmB);
-    for (int i = 0; i < nst; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], CM + CN - 1);  // one MMA-retire arrival from every CTA this CTA multicasts to
-    }
-    mbar_init(&tmem_full[0], 1);
-    mbar_init(&tmem_full[1], 1);
-    mbar_init(&tmem_empty[0], kEpiWarps);
-    mbar_init(&tmem_empty[1], kEpiWarps);
-    for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&epi_bar[i], 1);
+  if (warp == 0) {
+    // one barrier per lane; contiguous array full[nst] empty[nst] tmem_full[2] tmem_empty[2] epi_bar[16]. empty: one MMA-retire
+    // arrival from every CTA this CTA multicasts to; tmem_empty: every epilogue warp
+    const int nbar = 2 * nst + 4 + 2 * kEpiWarps;
+    for (int i = lane; i < nbar; i += 32)
+      mbar_init(&full_bar[i], (i >= nst && i < 2 * nst) ? CM + CN - 1 : (i >= 2 * nst + 2 && i < 2 * nst + 4) ? kEpiWarps : 1);
     fence_barrier_init();
+    if (lane == 0) {
+      tma_prefetch_desc(&p.tmA0);
+      tma_prefetch_desc(&p.tmA1);
+      tma_prefetch_desc(&p.tmB);
+    }
   }
   if (warp == 1) tmem_alloc(tmem_ptr, tmem_cols);
   tc_fence_before();
@@ -735,7 +733,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   }
 
   if (dbg && threadIdx.x == 0) p.dbg[5] = globaltimer_ns();  // producer done issuing
-  if (p.epi_tma && warp >= 2 && lane == 0) bulk_wait_group_all();   // this thread's TMA stores have been written before the CTA retires
+  if (p.epi_tma && warp >= 2 && lane == 0) bulk_wait_group_read<0>();   // the TMA stores have read their shared-memory boxes; the writes complete with the grid
   tc_fence_before();
   __syncthreads();
   if (dbg && threadIdx.x == 0) p.dbg[6] = globaltimer_ns();  // all roles done
@@ -808,6 +806,7 @@ __device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {  // arrive on `b
 
 __global__ void __launch_bounds__(kThreads, 1) igemm_pair_kernel(const __grid_constant__ IgemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  if (p.dbg_all != nullptr && threadIdx.x == 0) p.dbg_all[blockIdx.x * 8 + 0] = globaltimer_ns();
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int BN = p.BN;
   const int nst = p.nstages;
@@ -836,23 +835,23 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_pair_kernel(const __grid_co
   uint32_t tmem_cols = 32;
   while (tmem_cols < (uint32_t)(2 * BN)) tmem_cols <<= 1;
 
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.tmA0);
-    tma_prefetch_desc(&p.tmA1);
-    tma_prefetch_desc(&p.tmB);
-    for (int i = 0; i < nst; ++i) {
-      mbar_init(&full_bar[i], 1);   // leader's producer arrives once with the byte count of both CTAs
-      mbar_init(&empty_bar[i], 1);  // leader's multicast commit
-    }
-    mbar_init(&tmem_full[0], 1);
-    mbar_init(&tmem_full[1], 1);
-    mbar_init(&tmem_empty[0], 2 * kEpiWarps);
-    mbar_init(&tmem_empty[1], 2 * kEpiWarps);
-    for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&epi_bar[i], 1);
+  if (warp == 0) {
+    // one barrier per lane (the ~30 barriers are one contiguous array: full[nst] empty[nst] tmem_full[2] tmem_empty[2] epi_bar[16]):
+    // full = the leader's producer arrives once with the byte count of both CTAs, empty = the leader's multicast commit,
+    // tmem_empty = every epilogue warp of both CTAs; a single lane initialising them one by one cost ~0.4 us of every launch
+    const int nbar = 2 * nst + 4 + 2 * kEpiWarps;
+    for (int i = lane; i < nbar; i += 32) mbar_init(&full_bar[i], (i >= 2 * nst + 2 && i < 2 * nst + 4) ? 2 * kEpiWarps : 1);
     fence_barrier_init();
+    if (lane == 0) {
+      tma_prefetch_desc(&p.tmA0);
+      tma_prefetch_desc(&p.tmA1);
+      tma_prefetch_desc(&p.tmB);
+    }
   }
   __syncthreads();
+  if (p.dbg_all != nullptr && threadIdx.x == 0) p.dbg_all[blockIdx.x * 8 + 1] = globaltimer_ns();
   cluster_sync_all();  // both CTAs' barriers exist before any cross-CTA signal
+  if (p.dbg_all != nullptr && threadIdx.x == 0) p.dbg_all[blockIdx.x * 8 + 2] = globaltimer_ns();
   if (warp == 1) tmem_alloc_pair(tmem_ptr, tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -861,9 +860,11 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_pair_kernel(const __grid_co
 
   const bool dbg = p.dbg != nullptr && blockIdx.x == 0;
   if (dbg && threadIdx.x == 0) p.dbg[0] = globaltimer_ns();   // prologue done (before griddep wait)
+  if (p.dbg_all != nullptr && threadIdx.x == 0) p.dbg_all[blockIdx.x * 8 + 3] = globaltimer_ns();
   griddep_wait();
   griddep_launch_dependents();
   if (dbg && threadIdx.x == 0) p.dbg[1] = globaltimer_ns();   // dependencies resolved
+  if (p.dbg_all != nullptr && threadIdx.x == 0) p.dbg_all[blockIdx.x * 8 + 4] = globaltimer_ns();
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs): warp-uniform loop, one elected lane issues =====================
@@ -1012,15 +1013,18 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_pair_kernel(const __grid_co
   }
 
   if (dbg && threadIdx.x == 0) p.dbg[5] = globaltimer_ns();  // producer done issuing
-  if (p.epi_tma && warp >= 2 && lane == 0) bulk_wait_group_all();   // this thread's TMA stores have been written before the CTA retires
+  if (p.dbg_all != nullptr && threadIdx.x == 64) p.dbg_all[blockIdx.x * 8 + 5] = globaltimer_ns();   // this warp's epilogue done
+  if (p.epi_tma && warp >= 2 && lane == 0) bulk_wait_group_read<0>();   // the TMA stores have read their shared-memory boxes; the writes complete with the grid
   tc_fence_before();
   __syncthreads();
+  if (p.dbg_all != nullptr && threadIdx.x == 0) p.dbg_all[blockIdx.x * 8 + 6] = globaltimer_ns();
   if (dbg && threadIdx.x == 0) p.dbg[6] = globaltimer_ns();  // all roles done
   cluster_sync_all();  // peer finished reading its TMEM / signalling our barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc_pair(tmem_base, tmem_cols);
   }
+  if (p.dbg_all != nullptr && threadIdx.x == 0) p.dbg_all[blockIdx.x * 8 + 7] = globaltimer_ns();
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -117,6 +117,7 @@ struct alignas(64) IgemmParams {
   unsigned fd_pm, fd_w, fd_h, fd_wh;   // divisors: pair M tiles (or M tiles), tilesW, tilesH, tilesW*tilesH
   int dbg_mode;               // diagnostics only: 1 = skip TMA loads, 2 = skip MMAs (results are garbage)
   unsigned long long* dbg;    // nullable: per-role %globaltimer stamps of CTA 0 (tools/igemm_timeline.py)
+  unsigned long long* dbg_all;  // nullable: [gridDim.x][4] stamps of EVERY CTA (entry, prologue done, dependencies resolved, exit): launch ramp / drain
 };
 // A operand view: NHWC f16 tensor [Bn, H, W, C] with channel pitch `pitch` (elements, multiple of 8).
 int make_tmap_act(CUtensorMap* tm, const __half* base, int Bn, int H, int W, int C, int pitch, int Wt,
