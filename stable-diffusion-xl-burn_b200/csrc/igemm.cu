@@ -736,7 +736,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   if (p.epi_tma && warp >= 2 && lane == 0) bulk_wait_group_read<0>();   // the TMA stores have read their shared-memory boxes; the writes complete with the grid
   tc_fence_before();
   __syncthreads();
-  if (dbg && threadIdx.x == 0) p.dbg[6] = globaltimer_ns();  // all roles done
+  if (dbg && threadIdx.x == 0) p.dbg[6] = globaltimer_ns();  // producer warp arrived at the final barrier (the read may issue before the barrier completes)
   if (cs > 1) cluster_sync_all();  // no CTA leaves while a peer may still signal its barriers
   if (warp == 1) {
     tc_fence_after();
@@ -1018,7 +1018,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_pair_kernel(const __grid_co
   tc_fence_before();
   __syncthreads();
   if (p.dbg_all != nullptr && threadIdx.x == 0) p.dbg_all[blockIdx.x * 8 + 6] = globaltimer_ns();
-  if (dbg && threadIdx.x == 0) p.dbg[6] = globaltimer_ns();  // all roles done
+  if (dbg && threadIdx.x == 0) p.dbg[6] = globaltimer_ns();  // producer warp arrived at the final barrier (the read may issue before the barrier completes)
   cluster_sync_all();  // peer finished reading its TMEM / signalling our barriers
   if (warp == 1) {
     tc_fence_after();

@@ -10,7 +10,7 @@ import sdxl_b200  # noqa: E402
 ctx = sdxl_b200.Context(0)
 shapes = [(2048, 1280, 1280, 0, 1), (2048, 5120, 1280, 0, 1), (2048, 1280, 3840, 0, 0), (2048, 1280, 10240, 1, 0),
           (8192, 640, 640, 0, 1), (8192, 640, 5120, 1, 0), (2048, 11520, 1280, 0, 1), (154, 2048, 2560, 0, 0)]
-print("M K N geglu res | BN pair CMxCN nst | prologue->deps deps->first_data first_data->acc0 acc0->epi0 | roles_done kernel_total event_ns | MMA-ideal_ns")
+print("M K N geglu res | BN pair CMxCN nst | prologue->deps deps->first_data first_data->acc0 acc0->epi0 | producer_done(from prologue) producer_done(from deps) event_ns | MMA-ideal_ns")
 for M, K, N, g, r in shapes:
     st = (C.c_uint64 * 9)()
     ctx.check(ctx.lib.sdxl_dbg_igemm_timeline(ctx.h, M, K, N, g, r, st), "timeline")
