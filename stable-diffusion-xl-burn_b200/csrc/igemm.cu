@@ -131,6 +131,8 @@ static constexpr int kEpiTmaBufBytes = 4096;                               // on
 static constexpr int kEpiAreaBytes = kEpiWarps * 2 * kEpiTmaBufBytes;      // 65536 B: two boxes per epilogue warp (TMA epilogue); the
                                                                           // transposing epilogue uses the first kEpiStageBytes of it
 static_assert(kEpiStageBytes <= kEpiAreaBytes, "staging area too small");
+// f16 outputs on the TMA epilogue use 32-row x 64-byte boxes: half the area (p.epi_box_bytes = 2048), which buys one more pipeline stage
+__host__ __device__ constexpr int epi_area_bytes(int box_bytes) { return kEpiWarps * 2 * box_bytes; }
 
 struct EpiRow {          // per-lane description of "my" accumulator row (lane = row within the warp's 32 rows)
   size_t pix;            // pixel (row of the output matrix)
@@ -527,7 +529,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   const int nst = p.nstages;
   const uint32_t stage_bytes = kABytes + BN * 128;
   uint8_t* epi_area = smem + (size_t)nst * stage_bytes;   // 1024 B aligned (stage sizes are multiples of 1 KB): epilogue boxes / staging
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_area + kEpiAreaBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_area + epi_area_bytes(p.epi_box_bytes));
   uint64_t* empty_bar = full_bar + nst;
   uint64_t* tmem_full = empty_bar + nst;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;    // [2]
@@ -669,8 +671,8 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     const int bt = r / (p.Wt * p.Ht);
     float* stage_buf = epi_stage + (warp - 2) * (32 * kStagePitch);
     EpiTma et;
-    et.box[0] = smem_u32(epi_area) + (uint32_t)((warp - 2) * 2) * kEpiTmaBufBytes;
-    et.box[1] = et.box[0] + kEpiTmaBufBytes;
+    et.box[0] = smem_u32(epi_area) + (uint32_t)((warp - 2) * 2) * (uint32_t)p.epi_box_bytes;
+    et.box[1] = et.box[0] + (uint32_t)p.epi_box_bytes;
     et.bar[0] = smem_u32(&epi_bar[(warp - 2) * 2]);
     et.bar[1] = et.bar[0] + 8;
     et.kb = 0;
@@ -813,7 +815,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_pair_kernel(const __grid_co
   const int b_rows = BN >> 1;                                  // this CTA's half of the B tile
   const uint32_t stage_bytes = kABytes + b_rows * 128;
   uint8_t* epi_area = smem + (size_t)nst * stage_bytes;   // 1024 B aligned (stage sizes are multiples of 1 KB): epilogue boxes / staging
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_area + kEpiAreaBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_area + epi_area_bytes(p.epi_box_bytes));
   uint64_t* empty_bar = full_bar + nst;
   uint64_t* tmem_full = empty_bar + nst;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;    // [2]  (used in the leader)
@@ -944,8 +946,8 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_pair_kernel(const __grid_co
     const int bt = r / (p.Wt * p.Ht);
     float* stage_buf = epi_stage + (warp - 2) * (32 * kStagePitch);
     EpiTma et;
-    et.box[0] = smem_u32(epi_area) + (uint32_t)((warp - 2) * 2) * kEpiTmaBufBytes;
-    et.box[1] = et.box[0] + kEpiTmaBufBytes;
+    et.box[0] = smem_u32(epi_area) + (uint32_t)((warp - 2) * 2) * (uint32_t)p.epi_box_bytes;
+    et.box[1] = et.box[0] + (uint32_t)p.epi_box_bytes;
     et.bar[0] = smem_u32(&epi_bar[(warp - 2) * 2]);
     et.bar[1] = et.bar[0] + 8;
     et.kb = 0;
@@ -1180,8 +1182,8 @@ static int device_sms() {
   return D ? D->num_sms : 148;
 }
 
-static size_t igemm_smem_bytes(int nst, int b_rows) {
-  return (size_t)nst * (kABytes + b_rows * 128) + 1024 /*align slack*/ + (2 * nst + 4 + 2 * kEpiWarps) * 8 + 32 + kEpiAreaBytes;
+static size_t igemm_smem_bytes(int nst, int b_rows, int epi_box_bytes) {
+  return (size_t)nst * (kABytes + b_rows * 128) + 1024 /*align slack*/ + (2 * nst + 4 + 2 * kEpiWarps) * 8 + 32 + epi_area_bytes(epi_box_bytes);
 }
 
 int igemm_configure(IgemmParams& p, const IgemmOperands& o, int outW, int outH, int outB, int mode, int geglu_bn) {
@@ -1242,6 +1244,7 @@ int igemm_configure(IgemmParams& p, const IgemmOperands& o, int outW, int outH, 
   if (nst > 8) nst = 8;
   if (nst < 2) nst = 2;
   p.nstages = nst;
+  p.epi_box_bytes = kEpiTmaBufBytes;
   // TMA epilogue: LINEAR tiles, 32-column blocks, tile rows = contiguous output rows (full image rows per tile and either whole
   // images or a single image per tile), f32 output (+ optional f32 residual of the same leading dimension) or f16 output without
   // residual. SDXL_B200_EPI_TMA=0 keeps the transposing epilogue everywhere (A/B).
@@ -1267,6 +1270,13 @@ int igemm_configure(IgemmParams& p, const IgemmOperands& o, int outW, int outH, 
     p.tmRes = p.tmOut;
     p.epi_tma = 1;
   }
+  // f16 outputs through TMA boxes of 64-byte rows: half the epilogue area, one more pipeline stage (SDXL_B200_EPI_COMPACT=0: A/B)
+  static const bool compact_on = !(getenv("SDXL_B200_EPI_COMPACT") && getenv("SDXL_B200_EPI_COMPACT")[0] == '0');
+  if (compact_on && p.epi_tma && !p.out_f32) {
+    p.epi_box_bytes = kEpiTmaBufBytes / 2;
+    int n2 = (226 * 1024 - 1024 - 512 - epi_area_bytes(p.epi_box_bytes)) / stage_bytes;
+    p.nstages = n2 > 8 ? 8 : n2;
+  }
   return 0;
 }
 
@@ -1274,8 +1284,11 @@ int igemm_launch(cudaStream_t st, IgemmParams& p) {
   // the epilogue addresses outputs with 32-bit element offsets and shares the leading dimension with the residual
   if (p.res != nullptr && p.ldr != p.ldo) return 1003;
   if ((unsigned long long)p.Bn * p.H * (unsigned long long)p.opix_row * (unsigned long long)p.ldo >= (1ull << 32)) return 1004;
-  const size_t smem = igemm_smem_bytes(p.nstages, p.pair ? p.BN / 2 : p.BN);
-  if (p.epi_tma && (p.opix_w != 1 || p.opix_off != 0 || p.opix_row != p.W)) p.epi_tma = 0;   // re-mapped output pixels (phase-decomposed upsample conv)
+  const size_t smem = igemm_smem_bytes(p.nstages, p.pair ? p.BN / 2 : p.BN, p.epi_box_bytes);
+  if (p.epi_tma && (p.opix_w != 1 || p.opix_off != 0 || p.opix_row != p.W)) {   // re-mapped output pixels (phase-decomposed upsample conv)
+    if (p.epi_box_bytes != kEpiTmaBufBytes) return 1011;   // the transposing epilogue needs the full staging area
+    p.epi_tma = 0;
+  }
   IgemmDev* D = igemm_dev();
   if (!D) return 1009;
   if (!D->attr) {

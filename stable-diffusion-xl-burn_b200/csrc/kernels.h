@@ -112,6 +112,7 @@ struct alignas(64) IgemmParams {
   // [pixels, ldo] output (N and BN multiples of 32, LINEAR mode); igemm_launch drops it if the caller re-mapped the output pixels.
   CUtensorMap tmOut, tmRes;   // 2-D [pixels, ldo] views, box 32 rows x 32 columns (f32: SWIZZLE_128B, f16: SWIZZLE_64B)
   int epi_tma;
+  int epi_box_bytes;          // bytes of one epilogue box in shared memory: 4096 (32 rows x 128 B), or 2048 for f16 outputs on the TMA epilogue
   // host-computed reciprocals (floor(2^32/d)+1; q = umulhi(n, m), exact while n*d < 2^32; 0 = use '/') for the tile-index
   // divisions of the producer warp: on the critical path between griddepcontrol.wait and the first TMA issue
   unsigned fd_pm, fd_w, fd_h, fd_wh;   // divisors: pair M tiles (or M tiles), tilesW, tilesH, tilesW*tilesH
