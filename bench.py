@@ -358,7 +358,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         "frac_vs_burst": ach / peaks["tflops_burst"], "peak_burst": peaks["tflops_burst"],
         # dram__bytes_read+write of the largest igemm launch (FF-in GEGLU, M=2048 N=10240 K=1280; algorithmic bytes
         # 26.2 MB weights + 5.2 MB activations in + 21 MB out) from the ncu --set full capture under profiles/
-        "traffic": 32.86e6, "traffic_unit": "bytes/launch (ncu --set full, profiles/r2_ncu_full_igemm.csv: FF-in GEGLU launch, 31.57 MB read + 1.29 MB written, tensor pipe 71.6 % active; algorithmic operand bytes 31.4 MB: the weights stream once)",
+        "traffic": 32.63e6, "traffic_unit": "bytes/launch (ncu --set full, profiles/r2_ncu_full_igemm.csv: FF-in GEGLU launch, 31.57 MB read + 1.05 MB written, tensor pipe 72.3 % active; algorithmic operand bytes 31.4 MB: the weights stream once)",
         "kernel": "igemm_pair_kernel / igemm_kernel (tcgen05 implicit GEMM: all Linear + conv of the step)",
         "peak_source": peaks["src"],
         "how": "algorithmic FLOPs of the step's igemm launches / (their share of an eager CUDA-event profile of the same plan x the measured graph step)",

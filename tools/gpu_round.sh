@@ -3,6 +3,7 @@
 # list of one timed step + `--set full` captures of the tensor-core kernels and of the HBM-bound kernels.  bash tools/gpu_round.sh <tag> [noncu]
 mkdir -p gpurun_out
 R=${1:-r2}
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
 timeout 2400 python -m pytest tests -q -m gpu -s 2>&1 | tail -150 > gpurun_out/pytest_gpu_$R.log
 echo "== pytest: $(tail -1 gpurun_out/pytest_gpu_$R.log)"; grep -E "PARITY|FAILED" gpurun_out/pytest_gpu_$R.log
 timeout 900 python bench.py --dump-ops gpurun_out/ops_$R.csv > gpurun_out/bench_$R.json 2> gpurun_out/bench_$R.err
