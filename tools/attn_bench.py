@@ -3,7 +3,7 @@
 
     python tools/attn_bench.py [out.json]
 
-For each (T, S, heads) of the step it reports the mean CUDA-event time of `sdxl_qkv_attention` over 20 launches (inputs rotate through 4 buffers; outputs are checked
+For each (T, S, heads) of the step it reports the median CUDA-event time of `sdxl_qkv_attention` over 20 back-to-back launches (inputs rotate through 4 buffers; outputs are checked
 against a float32 torch reference on the same device), the algorithmic TFLOP/s (4*B*T*S*C) and the fraction of the
 measured tensor peak. `per_step_ms` weights the shapes by how often one sampler step launches them (60/10/60/10).
 """
@@ -42,19 +42,18 @@ def main():
             for i in range(24):
                 ctx.qkv_attention(qs[i % 4], ks[i % 4], vs[i % 4], None, nh)
             torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             n = 20
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+            outs = [torch.empty(B, T, C, device="cuda", dtype=torch.float16) for _ in range(n)]
             ctx.enter()
-            e0.record(ctx.stream)
-            outs = []
+            ev[0].record(ctx.stream)
             for i in range(n):
-                o = torch.empty(B, T, C, device="cuda", dtype=torch.float16)
-                rc = lib.sdxl_qkv_attention(ctx.h, qs[i % 4].data_ptr(), ks[i % 4].data_ptr(), vs[i % 4].data_ptr(), None, B, T, S, C, nh, o.data_ptr())
+                rc = lib.sdxl_qkv_attention(ctx.h, qs[i % 4].data_ptr(), ks[i % 4].data_ptr(), vs[i % 4].data_ptr(), None, B, T, S, C, nh, outs[i].data_ptr())
                 assert rc == 0
-                outs.append(o)
-            e1.record(ctx.stream)
+                ev[i + 1].record(ctx.stream)
             ctx.synchronize()
-            us = e0.elapsed_time(e1) * 1e3 / n
+            per = sorted(ev[i].elapsed_time(ev[i + 1]) * 1e3 for i in range(n))
+            us = per[n // 2]   # median launch: a one-off stall (clock ramp, first use of a shape) must not decide the number
             fl = 4.0 * B * T * S * C
             rows.append({"T": T, "S": S, "heads": nh, "us": round(us, 2), "tflops": round(fl / us * 1e-6, 1), "rel_err_vs_f32": err})
             per_step += us * count * 1e-3
