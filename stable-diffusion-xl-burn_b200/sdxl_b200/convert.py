@@ -97,8 +97,8 @@ def write_npy_tree(weights: Dict[str, torch.Tensor], root: str, alphas_root: Opt
 
 
 def _main(argv=None) -> int:
-    """`python -m sdxl_b200.convert <model> <npy tree root> <out.pack>` — the role of the reference's `convert` binary
-    (src/bin/convert/main.rs) for this library's pack format. model: unet_base | unet_refiner | vae | clip_l | open_clip_g."""
+    """`python -m sdxl_b200.convert <model> <npy tree root> <out.pack> [--to-mpk STEM | --from-mpk STEM]` — the role of the reference's
+    `convert` binary (src/bin/convert/main.rs) for this library's pack format, plus both directions of its burn record. model: unet_base | unet_refiner | vae | clip_l | open_clip_g."""
     import argparse
     from .config import SDXL_BASE, SDXL_CLIP_L, SDXL_OPEN_CLIP_G, SDXL_REFINER, SDXL_VAE
     models = {"unet_base": SDXL_BASE, "unet_refiner": SDXL_REFINER, "vae": SDXL_VAE, "clip_l": SDXL_CLIP_L, "open_clip_g": SDXL_OPEN_CLIP_G}
@@ -107,8 +107,33 @@ def _main(argv=None) -> int:
     ap.add_argument("root", help="directory of the npy dump tree for this model (e.g. params/diffuser_base)")
     ap.add_argument("out", help="output pack file")
     ap.add_argument("--alphas-root", default=None, help="directory holding alphas_cumprod.npy (UNet only; default: parent of root)")
+    ap.add_argument("--from-mpk", metavar="STEM", default=None,
+                    help="UNet models: read the burn record <STEM>.mpk + <STEM>.cfg (the files the reference ships and loads, "
+                         "src/bin/sample/main.rs:28-51) instead of an npy tree; pass '-' as root")
+    ap.add_argument("--to-mpk", metavar="STEM", default=None,
+                    help="UNet models: also write <STEM>.mpk + <STEM>.cfg, i.e. what the reference's convert binary produces "
+                         "(src/bin/convert/main.rs:65-70)")
     a = ap.parse_args(argv)
-    pack = pack_from_npy_tree(a.root, models[a.model], a.alphas_root)
+    cfg = models[a.model]
+    is_unet = a.model.startswith("unet")
+    if (a.from_mpk or a.to_mpk) and not is_unet:
+        ap.error("--from-mpk / --to-mpk apply to the UNet (Diffuser) models")
+    if a.from_mpk:
+        from . import burn_record
+        from .weights import build_pack
+        rec_cfg, weights = burn_record.load_diffuser(a.from_mpk)
+        if rec_cfg != cfg:
+            ap.error(f"{a.from_mpk}.cfg describes {rec_cfg}, not {a.model}")
+        order = [name for name, _ in _specs(cfg)]   # the npy tree's order: the pack is then byte-identical to the one built from the tree
+        weights = {**{n: weights[n] for n in order if n in weights}, **{n: t for n, t in weights.items() if n not in order}}
+        pack = build_pack(weights)
+    else:
+        weights = load_npy_tree(a.root, cfg, a.alphas_root) if a.to_mpk else None
+        pack = pack_from_npy_tree(a.root, cfg, a.alphas_root)
+    if a.to_mpk:
+        from . import burn_record
+        burn_record.save_diffuser(a.to_mpk, cfg, weights)
+        print(f"wrote {a.to_mpk}.mpk, {a.to_mpk}.cfg")
     with open(a.out, "wb") as f:
         f.write(pack.numpy().tobytes())
     print(f"wrote {a.out}: {pack.numel()} bytes")

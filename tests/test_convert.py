@@ -55,3 +55,20 @@ def test_convert_cli_writes_the_same_pack(tmp_path, monkeypatch):
     out = str(tmp_path / "vae.pack")
     assert convert._main(["vae", root, out]) == 0
     assert open(out, "rb").read() == build_pack(w).numpy().tobytes()
+
+
+def test_convert_cli_burn_record_both_ways(tmp_path, monkeypatch):
+    """npy tree -> (--to-mpk) <stem>.mpk + .cfg, as the reference's convert binary does; then --from-mpk -> the same pack."""
+    from sdxl_b200 import TINY, convert, config
+    monkeypatch.setattr(config, "SDXL_BASE", TINY)
+    w = synth_weights(TINY, seed=4)
+    root, stem = str(tmp_path / "diffuser"), str(tmp_path / "rec" / "tiny")
+    os.makedirs(os.path.dirname(stem))
+    write_npy_tree(w, root)
+    out1, out2 = str(tmp_path / "a.pack"), str(tmp_path / "b.pack")
+    assert convert._main(["unet_base", root, out1, "--to-mpk", stem]) == 0
+    assert os.path.exists(stem + ".mpk") and os.path.exists(stem + ".cfg")
+    assert convert._main(["unet_base", "-", out2, "--from-mpk", stem]) == 0
+    assert open(out1, "rb").read() == open(out2, "rb").read() == build_pack(w).numpy().tobytes()
+    with pytest.raises(SystemExit):
+        convert._main(["vae", root, out1, "--to-mpk", stem])
