@@ -34,7 +34,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .config import UNetConfig
+from .config import ClipConfig, UNetConfig, VaeConfig
 
 Tree = Any
 
@@ -429,3 +429,191 @@ def save_diffuser(model_path: str, cfg: UNetConfig, weights: Dict[str, torch.Ten
     """Inverse of load_diffuser (what `convert` writes, src/bin/convert/main.rs:48-70)."""
     write_diffuser_cfg(model_path + ".cfg", cfg)
     write_mpk(model_path + ".mpk", weights_to_diffuser_record(cfg, weights))
+
+
+# ---------------------------------------------------------------------------------------------------
+# LatentDecoder record (src/model/stablediffusion/mod.rs:193-197: {autoencoder, scale_factor}) <-> dump-tree names of sdxl_vae_load
+# ---------------------------------------------------------------------------------------------------
+def _get_resnet_block(rec, out, path):     # autoencoder ResnetBlock (autoencoder/mod.rs:489-498)
+    _get_norm(rec["norm1"], out, f"{path}/norm1")
+    _get_linear(rec["conv1"], out, f"{path}/conv1")
+    _get_norm(rec["norm2"], out, f"{path}/norm2")
+    _get_linear(rec["conv2"], out, f"{path}/conv2")
+    if rec.get("nin_shortcut") is not None:
+        _get_linear(rec["nin_shortcut"], out, f"{path}/nin_shortcut")
+
+
+def _get_mid(rec, out, path):              # Mid (autoencoder/mod.rs:436-441) with ConvSelfAttentionBlock (:541-548)
+    _get_resnet_block(rec["block_1"], out, f"{path}/block_1")
+    _get_norm(rec["attn"]["norm"], out, f"{path}/attn/norm")
+    for n in ("q", "k", "v", "proj_out"):
+        _get_linear(rec["attn"][n], out, f"{path}/attn/{n}")
+    _get_resnet_block(rec["block_2"], out, f"{path}/block_2")
+
+
+def latent_decoder_record_to_weights(item: Tree) -> Dict[str, torch.Tensor]:
+    out: Dict[str, torch.Tensor] = {}
+    ae = item["autoencoder"]
+    _get_linear(ae["post_quant_conv"], out, "post_quant_conv")
+    d = ae["decoder"]
+    _get_linear(d["conv_in"], out, "decoder/conv_in")
+    _get_mid(d["mid"], out, "decoder/mid")
+    for i, b in enumerate(d["blocks"]):
+        for r in ("res1", "res2", "res3"):
+            _get_resnet_block(b[r], out, f"decoder/blocks/{i}/{r}")
+        if b.get("upsampler") is not None:
+            _get_linear(b["upsampler"], out, f"decoder/blocks/{i}/upsampler")
+    _get_norm(d["norm_out"], out, "decoder/norm_out")
+    _get_linear(d["conv_out"], out, "decoder/conv_out")
+    e = ae["encoder"]
+    _get_linear(e["conv_in"], out, "encoder/conv_in")
+    for i, b in enumerate(e["blocks"]):
+        for r in ("res1", "res2"):
+            _get_resnet_block(b[r], out, f"encoder/blocks/{i}/{r}")
+        if b.get("downsampler") is not None:          # PaddedConv2d {conv, kernel_size, stride, padding, padding_actual}
+            _get_linear(b["downsampler"]["conv"], out, f"encoder/blocks/{i}/downsampler/conv")
+    _get_mid(e["mid"], out, "encoder/mid")
+    _get_norm(e["norm_out"], out, "encoder/norm_out")
+    _get_linear(e["conv_out"], out, "encoder/conv_out")
+    _get_linear(ae["quant_conv"], out, "quant_conv")
+    return out
+
+
+def _put_resnet_block(w, path):
+    return {"norm1": _put_norm(w, f"{path}/norm1", True), "silu1": None, "conv1": _put_linear(w, f"{path}/conv1", True),
+            "norm2": _put_norm(w, f"{path}/norm2", True), "silu2": None, "conv2": _put_linear(w, f"{path}/conv2", True),
+            "nin_shortcut": _put_linear(w, f"{path}/nin_shortcut", True) if f"{path}/nin_shortcut/weight" in w else None}
+
+
+def _put_mid(w, path):
+    attn = {"norm": _put_norm(w, f"{path}/attn/norm", True)}
+    for n in ("q", "k", "v", "proj_out"):
+        attn[n] = _put_linear(w, f"{path}/attn/{n}", True)
+    return {"block_1": _put_resnet_block(w, f"{path}/block_1"), "attn": attn, "block_2": _put_resnet_block(w, f"{path}/block_2")}
+
+
+def weights_to_latent_decoder_record(w: Dict[str, torch.Tensor]) -> Tree:
+    def count(prefix):
+        i = 0
+        while f"{prefix}/{i}/res1/norm1/weight" in w:
+            i += 1
+        return i
+    dec_blocks = []
+    for i in range(count("decoder/blocks")):
+        bp = f"decoder/blocks/{i}"
+        dec_blocks.append({"res1": _put_resnet_block(w, f"{bp}/res1"), "res2": _put_resnet_block(w, f"{bp}/res2"), "res3": _put_resnet_block(w, f"{bp}/res3"),
+                           "upsampler": _put_linear(w, f"{bp}/upsampler", True) if f"{bp}/upsampler/weight" in w else None})
+    enc_blocks = []
+    for i in range(count("encoder/blocks")):
+        bp = f"encoder/blocks/{i}"
+        down = None
+        if f"{bp}/downsampler/conv/weight" in w:
+            down = {"conv": _put_linear(w, f"{bp}/downsampler/conv", True), "kernel_size": None, "stride": None,
+                    "padding": {"pad_left": None, "pad_right": None, "pad_top": None, "pad_bottom": None}, "padding_actual": None}
+        enc_blocks.append({"res1": _put_resnet_block(w, f"{bp}/res1"), "res2": _put_resnet_block(w, f"{bp}/res2"), "downsampler": down})
+    decoder = {"conv_in": _put_linear(w, "decoder/conv_in", True), "mid": _put_mid(w, "decoder/mid"), "blocks": dec_blocks,
+               "norm_out": _put_norm(w, "decoder/norm_out", True), "silu": None, "conv_out": _put_linear(w, "decoder/conv_out", True)}
+    encoder = {"conv_in": _put_linear(w, "encoder/conv_in", True), "mid": _put_mid(w, "encoder/mid"), "blocks": enc_blocks,
+               "norm_out": _put_norm(w, "encoder/norm_out", True), "silu": None, "conv_out": _put_linear(w, "encoder/conv_out", True)}
+    return {"autoencoder": {"encoder": encoder, "decoder": decoder, "quant_conv": _put_linear(w, "quant_conv", True),
+                            "post_quant_conv": _put_linear(w, "post_quant_conv", True)}, "scale_factor": None}
+
+
+def _vae_config_from_weights(w: Dict[str, torch.Tensor], scale_factor: float) -> VaeConfig:
+    """The reference hard-codes the autoencoder widths (AutoencoderConfig::new()); here they are read off the tensors, so that a
+    reduced-width record (tests) and the real one both load."""
+    def chans(prefix):
+        out, i = [], 0
+        while f"{prefix}/{i}/res1/conv1/weight" in w:
+            t = w[f"{prefix}/{i}/res1/conv1/weight"]
+            out.append((int(t.shape[1]), int(t.shape[0])))
+            i += 1
+        return tuple(out)
+    ng = 32
+    return VaeConfig(block_channels=chans("decoder/blocks"), latent_channels=int(w["post_quant_conv/weight"].shape[0]), n_group=ng,
+                     scale_factor=float(scale_factor), enc_block_channels=chans("encoder/blocks"), enc_z_channels=int(w["quant_conv/weight"].shape[0]))
+
+
+def load_latent_decoder(model_path: str) -> Tuple[VaeConfig, Dict[str, torch.Tensor]]:
+    """== load_latent_decoder_model (src/bin/sample/main.rs:43-51): `<path>.cfg` ({"scale_factor": ..}, LatentDecoderConfig,
+    stablediffusion/mod.rs:176-179) + `<path>.mpk` -> VaeConfig and weights in the names sdxl_vae_load / LatentDecoder(...) take."""
+    with open(model_path + ".cfg") as fh:
+        d = json.load(fh)
+    if "scale_factor" not in d:
+        raise BurnRecordError(f"{model_path}.cfg: LatentDecoderConfig key 'scale_factor' missing")
+    _, item = read_mpk(model_path + ".mpk")
+    w = latent_decoder_record_to_weights(item)
+    return _vae_config_from_weights(w, d["scale_factor"]), w
+
+
+def save_latent_decoder(model_path: str, cfg: VaeConfig, weights: Dict[str, torch.Tensor]) -> None:
+    with open(model_path + ".cfg", "w") as fh:
+        json.dump({"scale_factor": cfg.scale_factor}, fh)
+    write_mpk(model_path + ".mpk", weights_to_latent_decoder_record(weights))
+
+
+# ---------------------------------------------------------------------------------------------------
+# Embedder record (stablediffusion/mod.rs:652-658: {clip, open_clip, clip_tokenizer, open_clip_tokenizer}); the tokenizers carry no
+# parameters (they are rebuilt from the vocabulary files) and are skipped
+# ---------------------------------------------------------------------------------------------------
+def clip_record_to_weights(rec: Tree, where: str) -> Dict[str, torch.Tensor]:
+    """CLIP (src/model/clip/mod.rs:62-69) -> the names of sdxl_clip_load."""
+    out: Dict[str, torch.Tensor] = {}
+    out["token_embedding/weight"] = _tensor(rec["token_embedding"]["weight"], where + ".token_embedding")
+    out["position_embedding/weight"] = _tensor(rec["position_embedding"], where + ".position_embedding")
+    for i, b in enumerate(rec["blocks"]):
+        bp = f"blocks/{i}"
+        _get_norm(b["attn_ln"], out, f"{bp}/attn_ln")
+        _get_norm(b["mlp_ln"], out, f"{bp}/mlp_ln")
+        for n in ("query", "key", "value", "out"):
+            _get_linear(b["attn"][n], out, f"{bp}/attn/{n}")
+        _get_linear(b["mlp"]["fc1"], out, f"{bp}/mlp/fc1")
+        _get_linear(b["mlp"]["fc2"], out, f"{bp}/mlp/fc2")
+    _get_norm(rec["layer_norm"], out, "layer_norm")
+    if rec.get("text_projection") is not None:
+        out["text_projection"] = _tensor(rec["text_projection"], where + ".text_projection")
+    return out
+
+
+def weights_to_clip_record(w: Dict[str, torch.Tensor]) -> Tree:
+    blocks, i = [], 0
+    while f"blocks/{i}/attn_ln/weight" in w:
+        bp = f"blocks/{i}"
+        attn = {"n_head": None}
+        for n in ("query", "key", "value", "out"):
+            attn[n] = _put_linear(w, f"{bp}/attn/{n}")
+        blocks.append({"attn": attn, "attn_ln": _put_norm(w, f"{bp}/attn_ln", False),
+                       "mlp": {"quick_gelu": None, "fc1": _put_linear(w, f"{bp}/mlp/fc1"), "qgelu": None, "gelu": None, "fc2": _put_linear(w, f"{bp}/mlp/fc2")},
+                       "mlp_ln": _put_norm(w, f"{bp}/mlp_ln", False)})
+        i += 1
+    return {"token_embedding": {"weight": _param(w["token_embedding/weight"])}, "position_embedding": _param(w["position_embedding/weight"]),
+            "blocks": blocks, "layer_norm": _put_norm(w, "layer_norm", False),
+            "text_projection": _param(w["text_projection"]) if "text_projection" in w else None}
+
+
+def _clip_cfg(d: dict, where: str) -> ClipConfig:
+    try:
+        return ClipConfig(n_vocab=int(d["n_vocab"]), n_state=int(d["n_state"]), embed_dim=int(d["embed_dim"]), n_head=int(d["n_head"]), n_ctx=int(d["n_ctx"]),
+                          n_layer=int(d["n_layer"]), quick_gelu=bool(d["quick_gelu"]))
+    except KeyError as e:
+        raise BurnRecordError(f"{where}: CLIPConfig key {e} missing") from None
+
+
+def load_embedder(model_path: str) -> Tuple[ClipConfig, Dict[str, torch.Tensor], ClipConfig, Dict[str, torch.Tensor]]:
+    """== load_embedder_model (src/bin/sample/main.rs:28-33): EmbedderConfig JSON {clip_config, open_clip_config}
+    (stablediffusion/mod.rs:626-630) + record -> (CLIP-L config, weights, OpenCLIP config, weights) for ClipTextEncoder(...)."""
+    with open(model_path + ".cfg") as fh:
+        d = json.load(fh)
+    for k in ("clip_config", "open_clip_config"):
+        if k not in d:
+            raise BurnRecordError(f"{model_path}.cfg: EmbedderConfig key '{k}' missing")
+    _, item = read_mpk(model_path + ".mpk")
+    return (_clip_cfg(d["clip_config"], model_path + ".cfg"), clip_record_to_weights(item["clip"], "clip"),
+            _clip_cfg(d["open_clip_config"], model_path + ".cfg"), clip_record_to_weights(item["open_clip"], "open_clip"))
+
+
+def save_embedder(model_path: str, clip_cfg: ClipConfig, clip_w: Dict[str, torch.Tensor], open_cfg: ClipConfig, open_w: Dict[str, torch.Tensor]) -> None:
+    with open(model_path + ".cfg", "w") as fh:
+        json.dump({"clip_config": dict(clip_cfg.__dict__), "open_clip_config": dict(open_cfg.__dict__)}, fh)
+    write_mpk(model_path + ".mpk", {"clip": weights_to_clip_record(clip_w), "open_clip": weights_to_clip_record(open_w),
+                                    "clip_tokenizer": None, "open_clip_tokenizer": None})

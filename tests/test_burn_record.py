@@ -99,3 +99,23 @@ def test_inpaint_mask_rejects_bad_windows():
     for crop in ((10, 5, 0, 100), (0, 2000, 0, 100), (0, 100, 50, 50)):
         with pytest.raises(sdxl_b200.SdxlError):
             sdxl_b200.make_inpaint_mask((1024, 1024), (128, 128), *crop)
+
+
+def test_latent_decoder_and_embedder_records_round_trip(tmp_path):
+    """The other two files `sample` loads (src/bin/sample/main.rs:28-33, 43-51): LatentDecoder and Embedder records + their .cfg."""
+    from sdxl_b200 import TINY_CLIP, TINY_OPEN_CLIP, TINY_VAE
+    wv = synth_weights(TINY_VAE, seed=5)
+    BR.save_latent_decoder(str(tmp_path / "latent_decoder"), TINY_VAE, wv)
+    cfg, w2 = BR.load_latent_decoder(str(tmp_path / "latent_decoder"))
+    assert cfg == TINY_VAE                                  # widths are read off the tensors, scale_factor from the .cfg
+    assert set(w2) == set(wv) and all(torch.equal(w2[k], wv[k]) for k in wv)
+    wa, wb = synth_weights(TINY_CLIP, seed=6), synth_weights(TINY_OPEN_CLIP, seed=7)
+    BR.save_embedder(str(tmp_path / "embedder"), TINY_CLIP, wa, TINY_OPEN_CLIP, wb)
+    ca, ra, cb, rb = BR.load_embedder(str(tmp_path / "embedder"))
+    assert (ca, cb) == (TINY_CLIP, TINY_OPEN_CLIP)
+    for got, want in ((ra, wa), (rb, wb)):
+        assert set(got) == set(want) and all(torch.equal(got[k], want[k]) for k in want)
+    # a damaged config is an error, not a silent default
+    (tmp_path / "embedder.cfg").write_text('{"clip_config": {"n_vocab": 1}}')
+    with pytest.raises(BR.BurnRecordError):
+        BR.load_embedder(str(tmp_path / "embedder"))
