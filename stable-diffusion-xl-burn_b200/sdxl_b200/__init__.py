@@ -5,5 +5,5 @@ from ._lib import LIB_PATH, PROTOTYPES, SdxlError, SdxlLibraryMissing, load  # n
 from .engine import Conditioning, Context, Diffuser, LatentDecoder, ddim_timesteps  # noqa: F401
 from .tokenizer import ClipTokenizer, OpenClipTokenizer  # noqa: F401
 from .embedder import ClipTextEncoder, Embedder, conditioning_embedding  # noqa: F401
-from .pipeline import make_inpaint_mask, sample  # noqa: F401
+from .pipeline import load_models, make_inpaint_mask, sample  # noqa: F401
 from . import burn_record  # noqa: F401

@@ -617,3 +617,14 @@ def save_embedder(model_path: str, clip_cfg: ClipConfig, clip_w: Dict[str, torch
         json.dump({"clip_config": dict(clip_cfg.__dict__), "open_clip_config": dict(open_cfg.__dict__)}, fh)
     write_mpk(model_path + ".mpk", {"clip": weights_to_clip_record(clip_w), "open_clip": weights_to_clip_record(open_w),
                                     "clip_tokenizer": None, "open_clip_tokenizer": None})
+
+
+def read_model_dir(model_dir: str, use_refiner: bool = False) -> dict:
+    """The files of a reference download as `sample` addresses them (src/bin/sample/main.rs:156, 220, 242, 255, 274):
+    `<model_dir>/{embedder, diffuser, refiner, latent_decoder}.{mpk,cfg}` -> {"embedder": (clip cfg, weights, open_clip cfg, weights),
+    "diffuser": (cfg, weights), "refiner": (cfg, weights) | None, "latent_decoder": (cfg, weights)}. Host memory only."""
+    import os
+    return {"embedder": load_embedder(os.path.join(model_dir, "embedder")),
+            "diffuser": load_diffuser(os.path.join(model_dir, "diffuser")),
+            "refiner": load_diffuser(os.path.join(model_dir, "refiner")) if use_refiner else None,
+            "latent_decoder": load_latent_decoder(os.path.join(model_dir, "latent_decoder"))}

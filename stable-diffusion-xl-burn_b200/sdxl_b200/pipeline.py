@@ -46,3 +46,26 @@ def sample(embedder, diffuser, decoder, prompt: str, guidance: float = 7.5, n_st
     if refiner is not None:
         latent = refiner.refine_latent(latent, cond, guidance, REFINER_STEP_START, n_steps, seed=seed + 1)                    # main.rs:258-265
     return decoder.latent_to_image(latent)                                                                                   # main.rs:277
+
+
+def load_models(ctx, model_dir: str, use_refiner: bool = False, tokenizer_dir: str = "tokenizer", tokenizers=None):
+    """The four loads of the reference's `sample` (src/bin/sample/main.rs:156, 220, 242, 255, 274): `<model_dir>/embedder`,
+    `/diffuser`, `/refiner` (optional) and `/latent_decoder`, each a burn record `<name>.mpk` + `<name>.cfg`
+    (burn_record.read_model_dir); the tokenizers read `<tokenizer_dir>/clip/bpe_simple_vocab_16e6.txt` and
+    `<tokenizer_dir>/open_clip/{merges,vocab}.txt` like the reference (src/token/clip.rs:97, open_clip.rs:88-89) unless a
+    (clip, open_clip) pair is passed. Returns (embedder, diffuser, refiner | None, decoder), ready for `sample()`."""
+    import os
+    from . import burn_record as BR
+    from .embedder import ClipTextEncoder, Embedder
+    from .engine import Diffuser, LatentDecoder
+    from .tokenizer import ClipTokenizer, OpenClipTokenizer
+    files = BR.read_model_dir(model_dir, use_refiner)
+    if tokenizers is None:
+        tokenizers = (ClipTokenizer(os.path.join(tokenizer_dir, "clip", "bpe_simple_vocab_16e6.txt")),
+                      OpenClipTokenizer(os.path.join(tokenizer_dir, "open_clip", "merges.txt"), os.path.join(tokenizer_dir, "open_clip", "vocab.txt")))
+    ca, wa, cb, wb = files["embedder"]
+    emb = Embedder(ctx, ClipTextEncoder(ctx, ca, wa), ClipTextEncoder(ctx, cb, wb), tokenizers[0], tokenizers[1])
+    dif = Diffuser(ctx, *files["diffuser"])
+    ref = Diffuser(ctx, *files["refiner"]) if files["refiner"] is not None else None
+    dec = LatentDecoder(ctx, *files["latent_decoder"])
+    return emb, dif, ref, dec

@@ -119,3 +119,18 @@ def test_latent_decoder_and_embedder_records_round_trip(tmp_path):
     (tmp_path / "embedder.cfg").write_text('{"clip_config": {"n_vocab": 1}}')
     with pytest.raises(BR.BurnRecordError):
         BR.load_embedder(str(tmp_path / "embedder"))
+
+
+def test_read_model_dir_uses_the_sample_binarys_file_names(tmp_path):
+    from sdxl_b200 import TINY_CLIP, TINY_OPEN_CLIP, TINY_VAE
+    d = str(tmp_path)
+    BR.save_embedder(os.path.join(d, "embedder"), TINY_CLIP, synth_weights(TINY_CLIP, seed=1), TINY_OPEN_CLIP, synth_weights(TINY_OPEN_CLIP, seed=2))
+    BR.save_diffuser(os.path.join(d, "diffuser"), TINY, synth_weights(TINY, seed=3))
+    BR.save_latent_decoder(os.path.join(d, "latent_decoder"), TINY_VAE, synth_weights(TINY_VAE, seed=4))
+    files = BR.read_model_dir(d)
+    assert files["refiner"] is None and files["diffuser"][0] == TINY and files["latent_decoder"][0] == TINY_VAE
+    assert files["embedder"][0] == TINY_CLIP and files["embedder"][2] == TINY_OPEN_CLIP
+    with pytest.raises(FileNotFoundError):
+        BR.read_model_dir(d, use_refiner=True)             # <dir>/refiner.{cfg,mpk} absent
+    BR.save_diffuser(os.path.join(d, "refiner"), TINY_REFINER, synth_weights(TINY_REFINER, seed=5))
+    assert BR.read_model_dir(d, use_refiner=True)["refiner"][0] == TINY_REFINER

@@ -90,6 +90,17 @@ def test_text_to_image_and_inpaint(ctx):
     dif2 = Diffuser(ctx, cfg2, w2)
     assert torch.equal(dif2.sample_latent(cond, 5.0, 6, noise=noise), latent)
     dif2.close()
+    # a whole model directory as the reference's `sample` reads it (embedder / diffuser / latent_decoder records) -> same image
+    with tempfile.TemporaryDirectory() as td:
+        BR.save_embedder(os.path.join(td, "embedder"), CLIP_A, wa, CLIP_B, wb)
+        BR.save_diffuser(os.path.join(td, "diffuser"), UNET, wu)
+        BR.save_latent_decoder(os.path.join(td, "latent_decoder"), TINY_VAE, wv)
+        emb3, dif3, ref3, vae3 = sdxl_b200.load_models(ctx, td, tokenizers=(tok, tok))
+    assert ref3 is None
+    img4 = sdxl_b200.sample(emb3, dif3, vae3, text, guidance=5.0, n_steps=6, resolution=res, noise=noise)
+    assert torch.equal(img4, rgb)
+    for o in (emb3.clip, emb3.open_clip, dif3, vae3):
+        o.close()
     for o in (ea, eb, dif, vae):
         o.close()
 
